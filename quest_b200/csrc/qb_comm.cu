@@ -1,0 +1,198 @@
+// qb_comm.cu -- inter-GPU communication over NCCL (NVLink 5 / NVSwitch inside one 8xB200 box).
+// Replaces quest/src/comm/comm_config.cpp (MPI_Init/rank/size/barrier, :59-187) and
+// quest/src/comm/comm_routines.cpp (chunked Isend/Irecv exchange :209-232, Ibcast all-gather :292-349,
+// Allreduce :714-760, Bcast :632-695, Gather :786-812).  One process per GPU; ranks pair up as
+// rank ^ mask, and NVSwitch gives every pairing full bandwidth simultaneously, so no chunk-size
+// juggling against MPI's 2^31-element message limit (comm_routines.cpp:95) is needed.
+//
+// Amplitude traffic goes GPU-to-GPU directly: device pointers are handed to ncclSend/ncclRecv on the
+// library's compute stream, so an exchange is ordered after the kernels that produced its input and
+// before the kernels that consume its output without any host synchronisation (the reference
+// cudaDeviceSynchronize()s before every exchange, comm_routines.cpp:390).  Large exchanges are split
+// into chunks so that the consumer kernel of chunk i can overlap the transfer of chunk i+1
+// (qb_comm_exchange_chunked, used by the localiser shim).
+#include "qb_common.cuh"
+#include <nccl.h>
+#include <string.h>
+#include <vector>
+
+static ncclComm_t s_comm = nullptr;
+static int s_rank = 0, s_numRanks = 1;
+static bool s_init = false;
+static char* s_devScratch = nullptr;      // small device staging area for host-side collectives
+static char* s_hostScratch = nullptr;     // pinned
+static size_t s_scratchBytes = 0;
+
+static int nccl_error(ncclResult_t r, const char* what, const char* file, int line) {
+    char buf[512];
+    snprintf(buf, sizeof buf, "%s -> %s", what, ncclGetErrorString(r));
+    return qb_set_error(-1000 - (int)r, buf, file, line);
+}
+#define QB_NCCL(call) do { ncclResult_t r__ = (call); if (r__ != ncclSuccess) return nccl_error(r__, #call, __FILE__, __LINE__); } while (0)
+#define QB_COMM_READY() do { QB_READY(); QB_REQUIRE(s_init, "communicator not initialised (qb_comm_init)"); } while (0)
+
+static int ensureScratch(size_t bytes) {
+    if (bytes <= s_scratchBytes) return 0;
+    size_t want = bytes < (1u << 20) ? (1u << 20) : bytes;
+    QB_CUDA(cudaStreamSynchronize(g_qb.stream));
+    if (s_devScratch) cudaFree(s_devScratch);
+    if (s_hostScratch) cudaFreeHost(s_hostScratch);
+    s_devScratch = nullptr; s_hostScratch = nullptr; s_scratchBytes = 0;
+    QB_CUDA(cudaMalloc(&s_devScratch, want));
+    QB_CUDA(cudaMallocHost(&s_hostScratch, want));
+    s_scratchBytes = want;
+    return 0;
+}
+
+extern "C" {
+
+int qb_comm_get_unique_id(char id[QB_COMM_ID_BYTES]) {
+    static_assert(sizeof(ncclUniqueId) <= QB_COMM_ID_BYTES, "ncclUniqueId larger than QB_COMM_ID_BYTES");
+    ncclUniqueId uid;
+    QB_NCCL(ncclGetUniqueId(&uid));
+    memset(id, 0, QB_COMM_ID_BYTES);
+    memcpy(id, &uid, sizeof uid);
+    return 0;
+}
+
+int qb_comm_init(int rank, int numRanks, const char id[QB_COMM_ID_BYTES]) {
+    QB_REQUIRE(!s_init, "communicator already initialised");
+    QB_REQUIRE(numRanks >= 1 && rank >= 0 && rank < numRanks, "qb_comm_init: bad rank / size");
+    QB_REQUIRE((numRanks & (numRanks - 1)) == 0, "qb_comm_init: number of ranks must be a power of two");
+    // bind this process to "its" GPU before creating the communicator (gpu_config.cpp:332-353)
+    int nd = qb_num_devices();
+    QB_REQUIRE(nd > 0, "qb_comm_init: no CUDA device");
+    if (g_qb.device < 0) { int r = qb_bind_device(rank % nd); if (r) return r; }
+    ncclUniqueId uid;
+    memcpy(&uid, id, sizeof uid);
+    QB_NCCL(ncclCommInitRank(&s_comm, numRanks, uid, rank));
+    s_rank = rank; s_numRanks = numRanks; s_init = true;
+    return ensureScratch(1u << 20);
+}
+
+int qb_comm_end(void) {
+    if (!s_init) return 0;
+    cudaStreamSynchronize(g_qb.stream);
+    ncclCommDestroy(s_comm);
+    s_comm = nullptr; s_init = false; s_rank = 0; s_numRanks = 1;
+    return 0;
+}
+
+int qb_comm_is_init(void) { return s_init ? 1 : 0; }
+int qb_comm_rank(void) { return s_rank; }
+int qb_comm_num_ranks(void) { return s_numRanks; }
+
+int qb_comm_allreduce_sum(double* hostValues, qb_index n) {
+    QB_COMM_READY();
+    if (n <= 0) return 0;
+    size_t bytes = sizeof(double) * (size_t)n;
+    int r = ensureScratch(bytes); if (r) return r;
+    memcpy(s_hostScratch, hostValues, bytes);
+    QB_CUDA(cudaMemcpyAsync(s_devScratch, s_hostScratch, bytes, cudaMemcpyHostToDevice, g_qb.stream));
+    QB_NCCL(ncclAllReduce(s_devScratch, s_devScratch, (size_t)n, ncclDouble, ncclSum, s_comm, g_qb.stream));
+    QB_CUDA(cudaMemcpyAsync(s_hostScratch, s_devScratch, bytes, cudaMemcpyDeviceToHost, g_qb.stream));
+    QB_CUDA(cudaStreamSynchronize(g_qb.stream));
+    memcpy(hostValues, s_hostScratch, bytes);
+    return 0;
+}
+
+int qb_comm_barrier(void) {
+    QB_COMM_READY();
+    QB_CUDA(cudaDeviceSynchronize());
+    double x = 0;
+    return qb_comm_allreduce_sum(&x, 1);
+}
+
+int qb_comm_allreduce_and(int* hostFlag) {
+    QB_COMM_READY();
+    double v = *hostFlag ? 0.0 : 1.0;          // count the ranks on which the flag is false
+    int r = qb_comm_allreduce_sum(&v, 1); if (r) return r;
+    *hostFlag = (v == 0.0);
+    return 0;
+}
+
+int qb_comm_exchange(const qb_cplx* devSend, qb_cplx* devRecv, qb_index numAmps, int pairRank) {
+    QB_COMM_READY();
+    QB_REQUIRE(pairRank >= 0 && pairRank < s_numRanks && pairRank != s_rank, "exchange: bad pair rank");
+    if (numAmps <= 0) return 0;
+    QB_NCCL(ncclGroupStart());
+    QB_NCCL(ncclSend(devSend, (size_t)numAmps * 2, ncclDouble, pairRank, s_comm, g_qb.stream));
+    QB_NCCL(ncclRecv(devRecv, (size_t)numAmps * 2, ncclDouble, pairRank, s_comm, g_qb.stream));
+    QB_NCCL(ncclGroupEnd());
+    return 0;
+}
+
+int qb_comm_send(const qb_cplx* devSend, qb_index numAmps, int pairRank) {
+    QB_COMM_READY();
+    QB_REQUIRE(pairRank >= 0 && pairRank < s_numRanks && pairRank != s_rank, "send: bad pair rank");
+    if (numAmps <= 0) return 0;
+    QB_NCCL(ncclSend(devSend, (size_t)numAmps * 2, ncclDouble, pairRank, s_comm, g_qb.stream));
+    return 0;
+}
+
+int qb_comm_recv(qb_cplx* devRecv, qb_index numAmps, int pairRank) {
+    QB_COMM_READY();
+    QB_REQUIRE(pairRank >= 0 && pairRank < s_numRanks && pairRank != s_rank, "recv: bad pair rank");
+    if (numAmps <= 0) return 0;
+    QB_NCCL(ncclRecv(devRecv, (size_t)numAmps * 2, ncclDouble, pairRank, s_comm, g_qb.stream));
+    return 0;
+}
+
+int qb_comm_allgather(const qb_cplx* devSend, qb_cplx* devRecv, qb_index numAmpsPerRank) {
+    QB_COMM_READY();
+    if (numAmpsPerRank <= 0) return 0;
+    QB_NCCL(ncclAllGather(devSend, devRecv, (size_t)numAmpsPerRank * 2, ncclDouble, s_comm, g_qb.stream));
+    return 0;
+}
+
+int qb_comm_broadcast_bytes(void* hostBuf, size_t numBytes, int root) {
+    QB_COMM_READY();
+    if (numBytes == 0) return 0;
+    int r = ensureScratch(numBytes); if (r) return r;
+    if (s_rank == root) memcpy(s_hostScratch, hostBuf, numBytes);
+    QB_CUDA(cudaMemcpyAsync(s_devScratch, s_hostScratch, numBytes, cudaMemcpyHostToDevice, g_qb.stream));
+    QB_NCCL(ncclBroadcast(s_devScratch, s_devScratch, numBytes, ncclChar, root, s_comm, g_qb.stream));
+    QB_CUDA(cudaMemcpyAsync(s_hostScratch, s_devScratch, numBytes, cudaMemcpyDeviceToHost, g_qb.stream));
+    QB_CUDA(cudaStreamSynchronize(g_qb.stream));
+    memcpy(hostBuf, s_hostScratch, numBytes);
+    return 0;
+}
+
+int qb_comm_gather_bytes(const void* hostSend, void* hostRecvOnRoot, size_t numBytesPerRank, int root) {
+    QB_COMM_READY();
+    if (numBytesPerRank == 0) return 0;
+    size_t total = numBytesPerRank * (size_t)(s_numRanks + 1);
+    int r = ensureScratch(total); if (r) return r;
+    // layout: [own contribution][gathered numRanks contributions]
+    memcpy(s_hostScratch, hostSend, numBytesPerRank);
+    QB_CUDA(cudaMemcpyAsync(s_devScratch, s_hostScratch, numBytesPerRank, cudaMemcpyHostToDevice, g_qb.stream));
+    QB_NCCL(ncclAllGather(s_devScratch, s_devScratch + numBytesPerRank, numBytesPerRank, ncclChar, s_comm, g_qb.stream));
+    QB_CUDA(cudaMemcpyAsync(s_hostScratch + numBytesPerRank, s_devScratch + numBytesPerRank,
+                            numBytesPerRank * s_numRanks, cudaMemcpyDeviceToHost, g_qb.stream));
+    QB_CUDA(cudaStreamSynchronize(g_qb.stream));
+    if (s_rank == root && hostRecvOnRoot) memcpy(hostRecvOnRoot, s_hostScratch + numBytesPerRank, numBytesPerRank * s_numRanks);
+    return 0;
+}
+
+int qb_comm_sendrecv_host(const qb_cplx* hostSend, qb_cplx* hostRecv, qb_index numAmps, int sendRank, int recvRank) {
+    // comm_sendAmpsToRoot (comm_routines.cpp:643-671): sendRank's host array -> recvRank's host array
+    QB_COMM_READY();
+    if (numAmps <= 0 || sendRank == recvRank) return 0;
+    if (s_rank != sendRank && s_rank != recvRank) return 0;
+    size_t bytes = sizeof(qb_cplx) * (size_t)numAmps;
+    int r = ensureScratch(bytes); if (r) return r;
+    if (s_rank == sendRank) {
+        memcpy(s_hostScratch, hostSend, bytes);
+        QB_CUDA(cudaMemcpyAsync(s_devScratch, s_hostScratch, bytes, cudaMemcpyHostToDevice, g_qb.stream));
+        QB_NCCL(ncclSend(s_devScratch, (size_t)numAmps * 2, ncclDouble, recvRank, s_comm, g_qb.stream));
+        QB_CUDA(cudaStreamSynchronize(g_qb.stream));
+    } else {
+        QB_NCCL(ncclRecv(s_devScratch, (size_t)numAmps * 2, ncclDouble, sendRank, s_comm, g_qb.stream));
+        QB_CUDA(cudaMemcpyAsync(s_hostScratch, s_devScratch, bytes, cudaMemcpyDeviceToHost, g_qb.stream));
+        QB_CUDA(cudaStreamSynchronize(g_qb.stream));
+        memcpy(hostRecv, s_hostScratch, bytes);
+    }
+    return 0;
+}
+
+} // extern "C"

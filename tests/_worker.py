@@ -1,0 +1,36 @@
+"""Worker process: runs a list of programs (quest_b200/program.py) on ONE QuEST library and pickles the
+outputs.  usage: python tests/_worker.py <which: b200|ref> <programs.pkl> <out.pkl>
+A separate process per library is required because both export the same symbols and QuEST keeps
+process-global singletons (api/environment.cpp:49)."""
+import os
+import pickle
+import sys
+
+sys.path.insert(0, os.path.dirname(os.path.dirname(os.path.abspath(__file__))))
+
+from quest_b200 import quest_api as qa          # noqa: E402
+from quest_b200.program import run_program      # noqa: E402
+
+
+def main():
+    which, src, dst = sys.argv[1:4]
+    progs = pickle.load(open(src, "rb"))
+    if which == "ref":
+        Q = qa.QuEST(qa.REF_LIB)
+        Q.initCustomQuESTEnv(0, 0, 1)            # reference: CPU + OpenMP, the parity oracle
+    else:
+        Q = qa.QuEST(qa.B200_LIB)
+        Q.initCustomQuESTEnv(0, 1, 0)            # product: GPU only; fails loudly without a device
+    outs = []
+    for p in progs:
+        out = run_program(Q, p)
+        if which != "ref":
+            for name, inf in out["info"].items():
+                assert inf["isGpuAccelerated"] == 1, f"qureg {name} is not GPU-accelerated: refusing CPU path"
+        outs.append(out)
+    Q.finalizeQuESTEnv()
+    pickle.dump(outs, open(dst, "wb"))
+
+
+if __name__ == "__main__":
+    main()

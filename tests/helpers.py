@@ -1,0 +1,67 @@
+"""Shared test plumbing: run programs on a QuEST library in a worker process, compare outputs."""
+import os
+import pickle
+import subprocess
+import sys
+import tempfile
+
+import numpy as np
+
+ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+GOLDEN_DIR = os.path.join(ROOT, "tests", "golden")
+REF_LIB = os.path.join(ROOT, "oracle", "_ref", "libQuEST.so")
+B200_LIB = os.path.join(ROOT, "quest_b200", "lib", "libQuEST.so")
+
+# the north-star tolerance: 1e-12 relative L2 on amplitudes / expectation values in fp64
+TOL = 1e-12
+
+
+def run_programs(which, progs, timeout=1800, env=None):
+    """which: 'b200' (the product, GPU) or 'ref' (unmodified reference CPU build)."""
+    with tempfile.TemporaryDirectory() as d:
+        src, dst = os.path.join(d, "in.pkl"), os.path.join(d, "out.pkl")
+        pickle.dump(progs, open(src, "wb"))
+        e = dict(os.environ)
+        e.update(env or {})
+        r = subprocess.run([sys.executable, os.path.join(ROOT, "tests", "_worker.py"), which, src, dst],
+                           capture_output=True, text=True, timeout=timeout, env=e)
+        if r.returncode != 0 or not os.path.exists(dst):
+            raise RuntimeError(f"worker({which}) failed rc={r.returncode}\nstdout:\n{r.stdout[-3000:]}\nstderr:\n{r.stderr[-3000:]}")
+        return pickle.load(open(dst, "rb"))
+
+
+def rel_l2(a, b):
+    a, b = np.asarray(a, dtype=np.complex128).ravel(), np.asarray(b, dtype=np.complex128).ravel()
+    denom = np.linalg.norm(b)
+    return float(np.linalg.norm(a - b) / (denom if denom > 0 else 1.0))
+
+
+def flatten_result(r):
+    if r is None or isinstance(r, str):
+        return None
+    return np.asarray(r, dtype=np.float64).ravel()
+
+
+def assert_outputs_match(got, want, tol=TOL, label="", int_exact_ops=()):
+    """amplitude dumps: relative L2 <= tol; scalar results: |d| <= tol * max(1, |want|)."""
+    for name, w in want["dumps"].items():
+        g = got["dumps"][name]
+        assert g.shape == w.shape, f"{label} dump {name}: shape {g.shape} vs {w.shape}"
+        err = rel_l2(g, w)
+        assert err <= tol, f"{label} dump {name}: rel-L2 {err:.3e} > {tol:g}"
+    assert len(got["results"]) == len(want["results"])
+    for i, (g, w) in enumerate(zip(got["results"], want["results"])):
+        gf, wf = flatten_result(g), flatten_result(w)
+        if wf is None:
+            continue
+        assert gf is not None and gf.shape == wf.shape, f"{label} result {i}: {g} vs {w}"
+        if i in int_exact_ops:
+            assert np.array_equal(gf, wf), f"{label} result {i} (bit-exact): {g} vs {w}"
+            continue
+        scale = max(1.0, float(np.max(np.abs(wf)))) if wf.size else 1.0
+        err = float(np.max(np.abs(gf - wf))) if wf.size else 0.0
+        assert err <= tol * scale * 10, f"{label} result {i}: {g} vs {w} (abs err {err:.3e})"
+
+
+def load_golden(name):
+    return pickle.load(open(os.path.join(GOLDEN_DIR, name), "rb"))
