@@ -23,6 +23,11 @@ def main():
         Q.initCustomQuESTEnv(0, 1, 0)            # product: GPU only; fails loudly without a device
     outs = []
     for p in progs:
+        if which != "ref":
+            # small Quregs are auto-deployed to the CPU (core/autodeployer.hpp:17-21); the product under test
+            # is the GPU backend, so force GPU acceleration exactly as createCustomQureg allows a user to
+            for spec in p["quregs"].values():
+                spec.setdefault("custom", [0, 1, 0])
         out = run_program(Q, p)
         if which != "ref":
             for name, inf in out["info"].items():

@@ -48,8 +48,8 @@ def test_debug_state_formula():
     # tests/utils/qvector.cpp:136-141: a_i = 2i/10 + i(2i+1)/10
     st = qo.new_state(4)
     qo.statevec_initDebugState_sub(st)
-    i = np.arange(16)
-    assert np.array_equal(st.amps, (2 * i) / 10. + 1j * (2 * i + 1) / 10.)
+    i = np.arange(16, dtype=np.float64)
+    assert np.array_equal(st.amps.real, (2 * i) / 10.) and np.array_equal(st.amps.imag, (2 * i + 1) / 10.)
 
 
 def test_insert_bits_matches_definition():
@@ -68,3 +68,14 @@ def test_insert_bits_matches_definition():
             want |= ((src >> pos) & 1) << b
             pos += 1
         assert got == want
+
+
+def test_debug_state_bit_exact_vs_reference():
+    """initDebugState is pure index arithmetic + two real divisions: the oracle must equal the reference BITWISE"""
+    fx = H.load_golden("gates_sv.pkl")
+    prog = {"quregs": {"psi": {"n": 6, "init": "debug"}}, "ops": [], "dump": ["psi"]}
+    got = run_program(prog)["dumps"]["psi"]
+    if os.path.exists(H.REF_LIB):
+        want = H.run_programs("ref", [prog])[0]["dumps"]["psi"]
+        assert np.array_equal(got, want)
+    assert fx["programs"][0]["quregs"]["psi"]["init"] == "debug"
