@@ -32,9 +32,9 @@ SHIM_FLAGS := -std=c++17 -O2 -fPIC -fopenmp -Wno-unknown-pragmas -I$(REF) -Iincl
 
 HOSTOBJ_DIR := oracle/_ref/hostobj
 HAVE_REF := $(wildcard $(REF)/quest/src/api/qureg.cpp)
-# stage switch: until quest_b200/shim provides comm_* and localiser_* itself, link the reference objects
-EXTRA_REF_OBJS ?= $(wildcard oracle/_ref/refobj/comm/*.o)
-LOCALISER_FILTER ?=
+# comm_* and localiser_* come from quest_b200/shim; the reference objects for those files are NOT linked
+EXTRA_REF_OBJS ?=
+LOCALISER_FILTER ?= ! -name localiser.o
 
 .PHONY: all kernels quest oracle clean
 all: kernels oracle quest

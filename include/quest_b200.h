@@ -224,6 +224,9 @@ int qb_densmatr_calcExpecFullStateDiagMatr_sub(const qb_state* q, const qb_cplx*
  * i^{numY_t}-free raw sum  sum_n (-1)^{popc(j&maskYZ)} conj(a_n) a_j , j = n ^ maskXY  (HOST out). */
 int qb_statevec_calcExpecPauliStrBatch_subA(const qb_state* q, const unsigned long long* masks,
         int numTerms, qb_cplx* outTerms);
+/* same with the partner amplitudes a_j read from the communication buffer (after a full exchange) */
+int qb_statevec_calcExpecPauliStrBatch_subB(const qb_state* q, const unsigned long long* masks,
+        int numTerms, qb_cplx* outTerms);
 
 /* ------------------------------------------------------------------------------------------
  * projectors                                 (gpu_subroutines.hpp:183-188)
@@ -264,6 +267,24 @@ int qb_comm_allreduce_and(int* hostFlag);                            /* comm_isT
 int qb_comm_broadcast_bytes(void* hostBuf, size_t numBytes, int rootRank); /* comm_broadcast*     :632-695 */
 int qb_comm_gather_bytes(const void* hostSend, void* hostRecvOnRoot, size_t numBytesPerRank, int rootRank);
 int qb_comm_sendrecv_host(const qb_cplx* hostSend, qb_cplx* hostRecv, qb_index numAmps, int sendRank, int recvRank);
+
+/* ------------------------------------------------------------------------------------------
+ * fused compute + exchange over NVLink peer memory (no reference equivalent: replaces the
+ * "exchange into buffer, then combine" pairs of core/localiser.cpp:854-869 and :941-953).
+ * The partner rank's amplitudes are mapped into this process with CUDA IPC; ONE kernel per GPU reads and
+ * writes both ranks' amplitudes, so no communication buffer, no pack/unpack pass and no combine pass exist,
+ * and the NVLink transfer overlaps the arithmetic element by element.  Both ranks of a pair must call the
+ * same function (SPMD); ordering between the two GPUs uses system-scope flags in IPC-shared memory.
+ * ---------------------------------------------------------------------------------------- */
+int qb_p2p_is_available(void);          /* 1 when comm is initialised and every peer's memory is mappable */
+int qb_p2p_set_enabled(int enabled);    /* 0 forces the NCCL exchange path (used by parity tests)          */
+/* gate on a PREFIX target: this rank holds target bit `rankBit`; pairRank holds the other half of every pair.
+ * matr = row-major 2x2.  ctrls are suffix controls. (localiser.cpp:941-953 + gpu_subroutines.cpp:319-345) */
+int qb_p2p_anyCtrlOneTargDenseMatr(const qb_state* q, const int* ctrls, const int* ctrlStates, int numCtrls,
+        int pairRank, int rankBit, const qb_cplx matr[4]);
+/* SWAP of a prefix qubit (partner = pairRank) with suffix qubit suffixTarg: the half-shards whose suffix
+ * bit differs from the rank bit trade places. (localiser.cpp:854-869 + gpu_subroutines.cpp:251-280) */
+int qb_p2p_swapHalves(const qb_state* q, int suffixTarg, int pairRank);
 
 #ifdef __cplusplus
 }

@@ -144,7 +144,7 @@ static int qb_hist(const HistArgs& a, int k, double* outProbs) {
 // sums in registers, the state element a_n is loaded once per group and its partners a_{n^maskXY} come
 // mostly from L2 (they lie in the same 2^k-aligned neighbourhood when the masks are low, else stream).
 #define QB_PAULI_BATCH 8
-struct PauliBatch { const cplx* amps; qindex maskXY[QB_PAULI_BATCH], maskYZ[QB_PAULI_BATCH]; int count; };
+struct PauliBatch { const cplx* amps; const cplx* other; qindex maskXY[QB_PAULI_BATCH], maskYZ[QB_PAULI_BATCH]; int count; };
 
 __global__ void __launch_bounds__(QB_BLOCK) k_pauliBatch(qindex numItems, PauliBatch pb, double* partials,
                                                         unsigned int* ticket, double* out) {
@@ -161,7 +161,7 @@ __global__ void __launch_bounds__(QB_BLOCK) k_pauliBatch(qindex numItems, PauliB
             if (t < pb.count) {
                 qindex j = n ^ pb.maskXY[t];
                 double s = 1.0 - 2.0 * parity64((unsigned long long)(j & pb.maskYZ[t]));
-                cplx y = pb.amps[j];
+                cplx y = pb.other[j];
                 re[t] += s * (x.x * y.x + x.y * y.y);
                 im[t] += s * (x.x * y.y - x.y * y.x);
             }
@@ -331,14 +331,16 @@ int qb_densmatr_calcExpecFullStateDiagMatr_sub(const qb_state* q, const qb_cplx*
     return qb_reduce2(pow2(q->logNumColsPerNode), f, &out->re, &out->im);
 }
 
-int qb_statevec_calcExpecPauliStrBatch_subA(const qb_state* q, const unsigned long long* masks, int numTerms, qb_cplx* outTerms) {
-    QB_READY(); QB_CHECK_STATE(q); QB_REQUIRE(masks && outTerms && numTerms >= 0, "pauli batch: bad arguments");
+} // extern "C"
+
+static int pauliBatch(const qb_state* q, const cplx* other, const unsigned long long* masks, int numTerms, qb_cplx* outTerms) {
+    QB_READY(); QB_CHECK_STATE(q); QB_REQUIRE(masks && outTerms && other && numTerms >= 0, "pauli batch: bad arguments");
     qindex blocks = (q->numAmpsPerNode + QB_BLOCK - 1) / QB_BLOCK;
     qindex maxBlocks = (qindex)g_qb.numSMs * 4;
     if (maxBlocks > QB_RED_MAX_BLOCKS) maxBlocks = QB_RED_MAX_BLOCKS;
     if (blocks > maxBlocks) blocks = maxBlocks;
     for (int base = 0; base < numTerms; base += QB_PAULI_BATCH) {
-        PauliBatch pb; pb.amps = (const cplx*)q->amps;
+        PauliBatch pb; pb.amps = (const cplx*)q->amps; pb.other = other;
         pb.count = numTerms - base < QB_PAULI_BATCH ? numTerms - base : QB_PAULI_BATCH;
         for (int t = 0; t < QB_PAULI_BATCH; t++) {
             bool live = t < pb.count;
@@ -354,6 +356,18 @@ int qb_statevec_calcExpecPauliStrBatch_subA(const qb_state* q, const unsigned lo
         for (int t = 0; t < pb.count; t++) { outTerms[base + t].re = g_qb.redOutHost[2 * t]; outTerms[base + t].im = g_qb.redOutHost[2 * t + 1]; }
     }
     return 0;
+}
+
+extern "C" {
+
+int qb_statevec_calcExpecPauliStrBatch_subA(const qb_state* q, const unsigned long long* masks, int numTerms, qb_cplx* outTerms) {
+    QB_REQUIRE(q, "null state");
+    return pauliBatch(q, (const cplx*)q->amps, masks, numTerms, outTerms);
+}
+
+int qb_statevec_calcExpecPauliStrBatch_subB(const qb_state* q, const unsigned long long* masks, int numTerms, qb_cplx* outTerms) {
+    QB_REQUIRE(q && q->buffer, "pauli batch subB: no communication buffer");
+    return pauliBatch(q, (const cplx*)q->buffer, masks, numTerms, outTerms);
 }
 
 } // extern "C"

@@ -196,3 +196,51 @@ int qb_comm_sendrecv_host(const qb_cplx* hostSend, qb_cplx* hostRecv, qb_index n
 }
 
 } // extern "C"
+
+// ------------------------------------------------------------------------------------------
+// internal host-side helpers for the peer-memory layer (qb_p2p.cu)
+// ------------------------------------------------------------------------------------------
+int qb_comm_internal_allgather_host(const void* send, void* recvAll, size_t bytesPerRank) {
+    QB_COMM_READY();
+    size_t total = bytesPerRank * (size_t)(s_numRanks + 1);
+    int r = ensureScratch(total); if (r) return r;
+    memcpy(s_hostScratch, send, bytesPerRank);
+    QB_CUDA(cudaMemcpyAsync(s_devScratch, s_hostScratch, bytesPerRank, cudaMemcpyHostToDevice, g_qb.stream));
+    QB_NCCL(ncclAllGather(s_devScratch, s_devScratch + bytesPerRank, bytesPerRank, ncclChar, s_comm, g_qb.stream));
+    QB_CUDA(cudaMemcpyAsync(s_hostScratch + bytesPerRank, s_devScratch + bytesPerRank, bytesPerRank * s_numRanks,
+                            cudaMemcpyDeviceToHost, g_qb.stream));
+    QB_CUDA(cudaStreamSynchronize(g_qb.stream));
+    memcpy(recvAll, s_hostScratch + bytesPerRank, bytesPerRank * s_numRanks);
+    return 0;
+}
+
+int qb_comm_internal_sendrecv_host(const void* send, void* recv, size_t bytes, int pairRank) {
+    QB_COMM_READY();
+    int r = ensureScratch(2 * bytes); if (r) return r;
+    memcpy(s_hostScratch, send, bytes);
+    QB_CUDA(cudaMemcpyAsync(s_devScratch, s_hostScratch, bytes, cudaMemcpyHostToDevice, g_qb.stream));
+    QB_NCCL(ncclGroupStart());
+    QB_NCCL(ncclSend(s_devScratch, bytes, ncclChar, pairRank, s_comm, g_qb.stream));
+    QB_NCCL(ncclRecv(s_devScratch + bytes, bytes, ncclChar, pairRank, s_comm, g_qb.stream));
+    QB_NCCL(ncclGroupEnd());
+    QB_CUDA(cudaMemcpyAsync(s_hostScratch + bytes, s_devScratch + bytes, bytes, cudaMemcpyDeviceToHost, g_qb.stream));
+    QB_CUDA(cudaStreamSynchronize(g_qb.stream));
+    memcpy(recv, s_hostScratch + bytes, bytes);
+    return 0;
+}
+
+// blocking rendezvous with a set of ranks (each of which names this rank in its own set): one grouped
+// NCCL send/recv of a byte per partner, so the order in which ranks list their partners cannot deadlock
+int qb_comm_internal_sync_with(const int* ranks, int numRanks) {
+    QB_COMM_READY();
+    if (numRanks <= 0) return 0;
+    int r = ensureScratch(2 * (size_t)s_numRanks + 16); if (r) return r;
+    QB_NCCL(ncclGroupStart());
+    for (int i = 0; i < numRanks; i++) {
+        QB_NCCL(ncclSend(s_devScratch + ranks[i], 1, ncclChar, ranks[i], s_comm, g_qb.stream));
+        QB_NCCL(ncclRecv(s_devScratch + s_numRanks + ranks[i], 1, ncclChar, ranks[i], s_comm, g_qb.stream));
+    }
+    QB_NCCL(ncclGroupEnd());
+    QB_CUDA(cudaStreamSynchronize(g_qb.stream));
+    return 0;
+}

@@ -37,6 +37,8 @@ struct QbRuntime {
 extern QbRuntime g_qb;
 
 int  qb_set_error(int code, const char* what, const char* file, int line);
+void qb_p2p_note_alloc(void* base, size_t bytes);   // qb_p2p.cu: allocation registry for IPC export
+int  qb_p2p_note_free(void* base);
 int  qb_ensure_ready();   // binds device 0 lazily, allocates scratch; returns 0 or error
 
 #define QB_CUDA(call) do { cudaError_t e__ = (call); if (e__ != cudaSuccess) \

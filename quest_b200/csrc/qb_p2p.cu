@@ -1,0 +1,218 @@
+// qb_p2p.cu -- fused compute + exchange over NVLink peer memory.
+//
+// One process per GPU.  Every amplitude allocation made through qb_alloc can be exported with CUDA IPC; the
+// first time a pair of ranks needs each other's amplitudes they trade IPC handles (over the NCCL control
+// plane) and map the partner's allocation with cudaIpcOpenMemHandle(..., LazyEnablePeerAccess).  After that,
+// a gate on a prefix (rank-bit) qubit is ONE kernel per GPU: each GPU owns half of the amplitude pairs, loads
+// its own element from local HBM and the partner's element straight over NVLink (coalesced 128-bit peer loads),
+// applies the 2x2 matrix and stores both results -- one locally, one through NVLink.  Compared with the
+// reference's "exchange the whole shard into the buffer, then combine" (core/localiser.cpp:941-953):
+//   * no communication buffer traffic (saves writing + re-reading B*N bytes of HBM per GPU),
+//   * no separate combine pass: the NVLink transfer overlaps the arithmetic element by element,
+//   * the link carries the same B*N bytes per direction, so the pass is purely NVLink-bound.
+// Cross-GPU ordering: system-scope epoch flags in an IPC-shared page per rank; a one-thread kernel publishes
+// "my stream reached this point" to the partner and waits for the partner's flag, before and after the fused
+// kernel (so neither GPU reads amplitudes the other is still producing, nor runs ahead of remote writes).
+#include "qb_common.cuh"
+#include "qb_kernels.cuh"
+#include <map>
+#include <vector>
+#include <string.h>
+
+int qb_comm_internal_allgather_host(const void* send, void* recvAll, size_t bytesPerRank);
+int qb_comm_internal_sendrecv_host(const void* send, void* recv, size_t bytes, int pairRank);
+int qb_comm_internal_sync_with(const int* ranks, int numRanks);
+
+#define QB_P2P_MAX_RANKS 64
+
+struct Alloc { size_t bytes; bool exported; };
+static std::map<uintptr_t, Alloc> s_allocs;                          // local allocations made by qb_alloc
+static std::map<std::pair<uintptr_t,int>, void*> s_peerBase;         // (local base, pair rank) -> mapped partner base
+
+static bool s_ready = false, s_enabled = true, s_triedInit = false;
+static unsigned long long* s_myFlags = nullptr;                       // [QB_P2P_MAX_RANKS] written by peers
+static unsigned long long* s_peerFlags[QB_P2P_MAX_RANKS] = {nullptr}; // mapped flag pages of every peer
+static unsigned long long s_epoch[QB_P2P_MAX_RANKS] = {0};
+
+void qb_p2p_note_alloc(void* base, size_t bytes) { s_allocs[(uintptr_t)base] = Alloc{bytes, false}; }
+
+// called by qb_free before cudaFree: unmap what we imported for this logical allocation, and -- if the memory
+// was exported -- make sure every importer has unmapped it before it is released (collective, like destroyQureg)
+int qb_p2p_note_free(void* base) {
+    auto it = s_allocs.find((uintptr_t)base);
+    if (it == s_allocs.end()) return 0;
+    // handle exchange is symmetric, so the ranks we imported from are exactly the ranks that imported ours:
+    // unmap theirs, then rendezvous with each of them so that nobody frees memory a partner still has mapped
+    std::vector<int> partners;
+    for (auto p = s_peerBase.begin(); p != s_peerBase.end(); ) {
+        if (p->first.first == (uintptr_t)base) { cudaIpcCloseMemHandle(p->second); partners.push_back(p->first.second); p = s_peerBase.erase(p); }
+        else ++p;
+    }
+    s_allocs.erase(it);
+    if (!partners.empty() && qb_comm_is_init()) return qb_comm_internal_sync_with(partners.data(), (int)partners.size());
+    return 0;
+}
+
+static int p2p_init() {
+    if (s_triedInit) return 0;
+    s_triedInit = true;
+    if (!qb_comm_is_init() || qb_comm_num_ranks() < 2 || qb_comm_num_ranks() > QB_P2P_MAX_RANKS) return 0;
+    const int P = qb_comm_num_ranks(), me = qb_comm_rank();
+    QB_CUDA(cudaMalloc(&s_myFlags, sizeof(unsigned long long) * QB_P2P_MAX_RANKS));
+    QB_CUDA(cudaMemset(s_myFlags, 0, sizeof(unsigned long long) * QB_P2P_MAX_RANKS));
+    cudaIpcMemHandle_t mine;
+    cudaError_t e = cudaIpcGetMemHandle(&mine, s_myFlags);
+    int ok = (e == cudaSuccess);
+    if (!ok) cudaGetLastError();
+    std::vector<cudaIpcMemHandle_t> all(P);
+    int r = qb_comm_internal_allgather_host(&mine, all.data(), sizeof mine); if (r) return r;
+    for (int p = 0; p < P && ok; p++) {
+        if (p == me) { s_peerFlags[p] = s_myFlags; continue; }
+        void* ptr = nullptr;
+        e = cudaIpcOpenMemHandle(&ptr, all[p], cudaIpcMemLazyEnablePeerAccess);
+        if (e != cudaSuccess) { cudaGetLastError(); ok = 0; break; }
+        s_peerFlags[p] = (unsigned long long*)ptr;
+    }
+    // every rank must agree, otherwise one side would wait for flags that never come
+    double bad = ok ? 0.0 : 1.0;
+    r = qb_comm_allreduce_sum(&bad, 1); if (r) return r;
+    s_ready = (bad == 0.0);
+    return 0;
+}
+
+static int peer_pointer(const void* localPtr, int pairRank, void** peerPtr) {
+    uintptr_t p = (uintptr_t)localPtr;
+    auto it = s_allocs.upper_bound(p);
+    QB_REQUIRE(it != s_allocs.begin(), "p2p: pointer was not allocated by qb_alloc");
+    --it;
+    QB_REQUIRE(p < it->first + it->second.bytes, "p2p: pointer was not allocated by qb_alloc");
+    uintptr_t base = it->first;
+    unsigned long long offset = p - base;
+    auto key = std::make_pair(base, pairRank);
+    auto found = s_peerBase.find(key);
+    if (found == s_peerBase.end()) {
+        struct Msg { cudaIpcMemHandle_t h; unsigned long long offset, bytes; } mine, theirs;
+        memset(&mine, 0, sizeof mine);
+        QB_CUDA(cudaIpcGetMemHandle(&mine.h, (void*)base));
+        mine.offset = offset; mine.bytes = it->second.bytes;
+        int r = qb_comm_internal_sendrecv_host(&mine, &theirs, sizeof mine, pairRank); if (r) return r;
+        QB_REQUIRE(theirs.offset == offset && theirs.bytes == mine.bytes, "p2p: partner's allocation does not mirror this rank's");
+        void* mapped = nullptr;
+        QB_CUDA(cudaIpcOpenMemHandle(&mapped, theirs.h, cudaIpcMemLazyEnablePeerAccess));
+        it->second.exported = true;
+        found = s_peerBase.emplace(key, mapped).first;
+    }
+    *peerPtr = (char*)found->second + offset;
+    return 0;
+}
+
+__global__ void k_pair_barrier(unsigned long long* peerSlot, volatile unsigned long long* mySlot, unsigned long long epoch) {
+    __threadfence_system();
+    *(volatile unsigned long long*)peerSlot = epoch;        // "my stream has reached epoch"
+    __threadfence_system();
+    while (*mySlot < epoch) { }
+    __threadfence_system();
+}
+
+static int pair_barrier(int pairRank) {
+    unsigned long long epoch = ++s_epoch[pairRank];
+    k_pair_barrier<<<1, 1, 0, g_qb.stream>>>(s_peerFlags[pairRank] + qb_comm_rank(), s_myFlags + pairRank, epoch);
+    QB_LAUNCH_CHECK();
+    return 0;
+}
+
+// MODE 0: 2x2 dense gate across the pair; MODE 1: swap.  Each item = one amplitude of mine + one of the partner's.
+struct P2POp { BitIns ins; qindex peerXor; int bit; cplx m00, m01, m10, m11; };
+
+template <int MODE, int ITEMS>
+__global__ void __launch_bounds__(QB_BLOCK) k_p2p_pair(cplx* __restrict__ mine, cplx* __restrict__ peer, qindex first, qindex count, const P2POp op) {
+    qindex idx[ITEMS];
+    cplx a[ITEMS], b[ITEMS];
+    const qindex base = (qindex)blockIdx.x * (QB_BLOCK * ITEMS) + threadIdx.x;
+#pragma unroll
+    for (int j = 0; j < ITEMS; j++) {
+        const qindex n = base + (qindex)j * QB_BLOCK;
+        if (ITEMS == 1 && n >= count) return;
+        idx[j] = op.ins(first + n);
+        a[j] = mine[idx[j]];
+        b[j] = peer[idx[j] ^ op.peerXor];
+    }
+#pragma unroll
+    for (int j = 0; j < ITEMS; j++) {
+        cplx outMine, outPeer;
+        if (MODE == 0) {
+            cplx a0 = op.bit ? b[j] : a[j], a1 = op.bit ? a[j] : b[j];
+            cplx n0 = cfma(op.m01, a1, cmul(op.m00, a0));
+            cplx n1 = cfma(op.m11, a1, cmul(op.m10, a0));
+            outMine = op.bit ? n1 : n0; outPeer = op.bit ? n0 : n1;
+        } else { outMine = b[j]; outPeer = a[j]; }
+        mine[idx[j]] = outMine;
+        peer[idx[j] ^ op.peerXor] = outPeer;
+    }
+    __threadfence_system();
+}
+
+template <int MODE>
+static int launch_pair(cplx* mine, cplx* peer, qindex first, qindex count, const P2POp& op) {
+    if (count <= 0) return 0;
+    constexpr int ITEMS = 4;
+    if (count >= (qindex)QB_BLOCK * ITEMS && count % (QB_BLOCK * ITEMS) == 0)
+        k_p2p_pair<MODE, ITEMS><<<qb_grid(count, ITEMS), QB_BLOCK, 0, g_qb.stream>>>(mine, peer, first, count, op);
+    else
+        k_p2p_pair<MODE, 1><<<qb_grid(count, 1), QB_BLOCK, 0, g_qb.stream>>>(mine, peer, first, count, op);
+    QB_LAUNCH_CHECK();
+    return 0;
+}
+
+// splits `total` work items between the two ranks of a pair: the rank with the smaller id takes the first half
+static void my_share(qindex total, int pairRank, qindex* first, qindex* count) {
+    bool low = qb_comm_rank() < pairRank;
+    qindex half = total / 2;
+    if (total == 1) { *first = 0; *count = low ? 1 : 0; return; }
+    *first = low ? 0 : half;
+    *count = low ? half : total - half;
+}
+
+extern "C" {
+
+int qb_p2p_is_available(void) {
+    if (!s_enabled) return 0;
+    if (!s_triedInit) { if (p2p_init()) return 0; }
+    return s_ready ? 1 : 0;
+}
+
+int qb_p2p_set_enabled(int enabled) { s_enabled = enabled != 0; return 0; }
+
+int qb_p2p_anyCtrlOneTargDenseMatr(const qb_state* q, const int* ctrls, const int* cs, int nc, int pairRank, int rankBit, const qb_cplx m[4]) {
+    QB_READY(); QB_CHECK_STATE(q); QB_CHECK_SUFFIX(ctrls, nc, q);
+    QB_REQUIRE(qb_p2p_is_available(), "p2p path is not available");
+    void* peer = nullptr;
+    int r = peer_pointer(q->amps, pairRank, &peer); if (r) return r;
+    P2POp op; op.ins = qb_make_ins(ctrls, cs, nc, nullptr, nullptr, 0); op.peerXor = 0; op.bit = rankBit;
+    op.m00 = mk(m[0]); op.m01 = mk(m[1]); op.m10 = mk(m[2]); op.m11 = mk(m[3]);
+    qindex first, count;
+    my_share(q->numAmpsPerNode >> nc, pairRank, &first, &count);
+    r = pair_barrier(pairRank); if (r) return r;
+    r = launch_pair<0>((cplx*)q->amps, (cplx*)peer, first, count, op); if (r) return r;
+    return pair_barrier(pairRank);
+}
+
+int qb_p2p_swapHalves(const qb_state* q, int suffixTarg, int pairRank) {
+    QB_READY(); QB_CHECK_STATE(q); QB_CHECK_SUFFIX(&suffixTarg, 1, q);
+    QB_REQUIRE(qb_p2p_is_available(), "p2p path is not available");
+    void* peer = nullptr;
+    int r = peer_pointer(q->amps, pairRank, &peer); if (r) return r;
+    // my amplitudes with suffix bit == !myBit trade places with the partner's amplitudes with suffix bit == myBit,
+    // where myBit is this rank's value of the prefix qubit: myBit = 1 iff rank > pairRank (they differ in that bit only)
+    int myBit = qb_comm_rank() > pairRank ? 1 : 0;
+    int st = !myBit;
+    P2POp op; op.ins = qb_make_ins(&suffixTarg, &st, 1, nullptr, nullptr, 0); op.peerXor = pow2(suffixTarg); op.bit = myBit;
+    op.m00 = op.m01 = op.m10 = op.m11 = mk(0, 0);
+    qindex first, count;
+    my_share(q->numAmpsPerNode / 2, pairRank, &first, &count);
+    r = pair_barrier(pairRank); if (r) return r;
+    r = launch_pair<1>((cplx*)q->amps, (cplx*)peer, first, count, op); if (r) return r;
+    return pair_barrier(pairRank);
+}
+
+} // extern "C"

@@ -185,6 +185,7 @@ qb_cplx* qb_alloc(qb_index numAmps, int* status) {
     cudaError_t e = cudaMalloc(&p, (size_t)numAmps * sizeof(qb_cplx));
     if (e == cudaErrorMemoryAllocation) { cudaGetLastError(); return nullptr; }  // soft failure, like gpu_config.cpp:406-413
     if (e != cudaSuccess) { int c = qb_set_error((int)e, "cudaMalloc", __FILE__, __LINE__); if (status) *status = c; return nullptr; }
+    qb_p2p_note_alloc(p, (size_t)numAmps * sizeof(qb_cplx));
     return (qb_cplx*)p;
 }
 
@@ -192,6 +193,7 @@ int qb_free(qb_cplx* p) {
     if (!p) return 0;
     QB_READY();
     QB_CUDA(cudaStreamSynchronize(g_qb.stream));
+    { int r = qb_p2p_note_free(p); if (r) return r; }
     QB_CUDA(cudaFree(p));
     return 0;
 }

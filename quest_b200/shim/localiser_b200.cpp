@@ -1,0 +1,1200 @@
+/* localiser_b200.cpp -- distribution logic of the B200 backend for ONE NVSwitch box (<= 8 GPUs).
+ *
+ * Defines every localiser_* symbol of quest/src/core/localiser.hpp (the 60 functions the API layer calls)
+ * and thereby replaces quest/src/core/localiser.cpp.  The state is sharded exactly like the reference
+ * (rank r owns global indices [r*N, (r+1)*N): the top log2(P) qubits are "prefix" qubits = bits of the rank,
+ * api/qureg.cpp:42-74), so layout, getters/setters and every result stay bit-compatible; what differs is HOW
+ * a rank obtains the amplitudes it needs:
+ *
+ *   reference                                               here
+ *   ------------------------------------------------------  ---------------------------------------------------
+ *   MPI Isend/Irecv in 2^28-amp chunks, host-staged unless  NCCL send/recv on device pointers, enqueued on the
+ *   CUDA-aware; cudaDeviceSynchronize before every          compute stream (ordered with the kernels, no host sync)
+ *   exchange (comm_routines.cpp:209-232, 384-407)
+ *   1-target dense gate on a prefix qubit: full-state       each GPU of the pair updates HALF of the amplitude pairs
+ *   exchange (B*N each way) then combine (localiser.cpp:     reading/writing the partner's amplitudes directly over
+ *   941-953)                                                NVLink inside ONE kernel: B*N/2 each way, no buffer,
+ *                                                           no pack/unpack (qb_p2p_*; NCCL path kept as fallback)
+ *   Pauli-sum expectation: one reduction pass per term      all terms of a prefix-XY group in batches of 8 per pass
+ *   (localiser.cpp:2097-2112)                               (qb_statevec_calcExpecPauliStrBatch_sub{A,B})
+ *
+ * Everything that is not communication is delegated to accel_* (core/accelerator.cpp, unchanged), so CPU-only
+ * Quregs keep working through the reference's own CPU path; distributed Quregs must be GPU-accelerated.
+ * The per-operator case analysis (which qubits are prefix, who is the pair rank, what is packed) follows the
+ * reference function cited at each definition.
+ */
+#include "quest/include/qureg.h"
+#include "quest/include/paulis.h"
+#include "quest/include/matrices.h"
+#include "quest/include/channels.h"
+#include "quest/include/initialisations.h"
+
+#include "quest/src/core/errors.hpp"
+#include "quest/src/core/bitwise.hpp"
+#include "quest/src/core/utilities.hpp"
+#include "quest/src/core/localiser.hpp"
+#include "quest/src/core/accelerator.hpp"
+#include "quest/src/comm/comm_config.hpp"
+#include "quest/src/comm/comm_routines.hpp"
+#include "quest/src/cpu/cpu_config.hpp"
+#include "quest/src/gpu/gpu_config.hpp"
+
+#include "quest_b200.h"
+
+#include <algorithm>
+#include <array>
+#include <complex>
+#include <map>
+#include <tuple>
+#include <vector>
+
+using std::vector;
+using std::tuple;
+
+// defined in api/paulis.cpp and api/qureg.cpp (unchanged reference host code)
+extern bool paulis_containsXOrY(PauliStr str);
+extern vector<int> paulis_getInds(PauliStr str);
+extern std::array<vector<int>,3> paulis_getSeparateInds(PauliStr str, Qureg qureg);
+extern int paulis_getPrefixZSign(Qureg qureg, vector<int> prefixZ);
+extern qcomp paulis_getPrefixPaulisElem(Qureg qureg, vector<int> prefixY, vector<int> prefixZ);
+extern PAULI_MASK_TYPE paulis_getKeyOfSameMixedAmpsGroup(PauliStr str);
+extern Qureg qureg_populateNonHeapFields(int numQubits, int isDensMatr, int useDistrib, int useGpuAccel, int useMultithread);
+
+#define QB_CHECK(call) qbLocCheck((call), #call, __func__, __FILE__, __LINE__)
+static void qbLocCheck(int status, const char* call, const char* caller, const char* file, int line) {
+    if (status != 0)
+        error_cudaCallFailed(qb_error_string(), call, caller, file, line);
+}
+
+
+/*
+ * SHARD ALGEBRA: where a qubit lives and who holds its partner amplitudes
+ */
+
+static bool isSuffix(Qureg q, int qubit) { return qubit < q.logNumAmpsPerNode; }
+
+static bool anyPrefix(Qureg q, const vector<int>& qubits) {
+    if (!q.isDistributed) return false;
+    for (int t : qubits) if (!isSuffix(q, t)) return true;
+    return false;
+}
+
+static int rankBit(Qureg q, int prefixQubit) { return getBit(q.rank, prefixQubit - (int) q.logNumAmpsPerNode); }
+
+static int rankWithFlipped(Qureg q, const vector<int>& prefixQubits) {
+    int r = q.rank;
+    for (int t : prefixQubits) r = flipBit(r, t - (int) q.logNumAmpsPerNode);
+    return r;
+}
+
+static bool braIsPrefix(Qureg q, int ket) { return q.isDistributed && !isSuffix(q, ket + q.numQubits); }
+
+// fills in default (all-1) control states, then drops the controls that are bits of the rank.
+// returns false when this rank holds no amplitude satisfying the prefix controls (it then has nothing to do)
+// [localiser.cpp:52-143: assertValidCtrlStates, setDefaultCtrlStates, doAnyLocalStatesHaveQubitValues, removePrefixQubitsAndStates]
+static bool localiseCtrls(Qureg q, vector<int>& ctrls, vector<int>& states) {
+    if (!states.empty() && states.size() != ctrls.size())
+        error_localiserNumCtrlStatesInconsistentWithNumCtrls();
+    if (states.empty())
+        states.assign(ctrls.size(), 1);
+    if (!q.isDistributed)
+        return true;
+    vector<int> c, s;
+    for (size_t i = 0; i < ctrls.size(); i++) {
+        if (isSuffix(q, ctrls[i])) { c.push_back(ctrls[i]); s.push_back(states[i]); }
+        else if (rankBit(q, ctrls[i]) != states[i]) return false;
+    }
+    ctrls = c; states = s;
+    return true;
+}
+
+static bool prefixValuesMatch(Qureg q, const vector<int>& qubits, const vector<int>& states) {
+    if (!q.isDistributed) return true;
+    for (size_t i = 0; i < qubits.size(); i++)
+        if (!isSuffix(q, qubits[i]) && rankBit(q, qubits[i]) != states[i]) return false;
+    return true;
+}
+
+static void keepSuffix(Qureg q, vector<int>& qubits, vector<int>& states) {
+    vector<int> c, s;
+    for (size_t i = 0; i < qubits.size(); i++)
+        if (isSuffix(q, qubits[i])) { c.push_back(qubits[i]); s.push_back(states[i]); }
+    qubits = c; states = s;
+}
+
+static qb_state toState(Qureg q) {
+    qb_state s;
+    s.amps = reinterpret_cast<qb_cplx*>(q.gpuAmps);
+    s.buffer = reinterpret_cast<qb_cplx*>(q.gpuCommBuffer);
+    s.numAmpsPerNode = q.numAmpsPerNode;
+    s.logNumAmpsPerNode = (int) q.logNumAmpsPerNode;
+    s.rank = q.rank;
+    s.numQubits = q.numQubits;
+    s.logNumColsPerNode = (int) q.logNumColsPerNode;
+    s.isDensityMatrix = q.isDensityMatrix;
+    return s;
+}
+
+
+/*
+ * SPOOFED VIEWS (localiser.cpp:264-440): Quregs / matrices aliasing existing memory with another deployment
+ */
+
+static Qureg viewLocalAsDistributed(Qureg local, Qureg distrib) {
+    assert_localiserDistribQuregSpooferGivenValidQuregs(local, distrib);
+    Qureg spoof = distrib;
+    qindex offset = util_getGlobalIndexOfFirstLocalAmp(distrib);
+    spoof.cpuAmps = &local.cpuAmps[offset];
+    spoof.gpuAmps = (local.isGpuAccelerated)? &local.gpuAmps[offset] : local.gpuAmps;
+    spoof.cpuCommBuffer = nullptr;
+    spoof.gpuCommBuffer = nullptr;
+    return spoof;
+}
+
+static FullStateDiagMatr viewLocalMatrAsDistributed(FullStateDiagMatr local, Qureg distrib) {
+    FullStateDiagMatr spoof = local;
+    spoof.isDistributed = 1;
+    spoof.numElemsPerNode = local.numElems / distrib.numNodes;
+    qindex offset = (distrib.isDensityMatrix)?
+        util_getGlobalColumnOfFirstLocalAmp(distrib):
+        util_getGlobalIndexOfFirstLocalAmp(distrib);
+    spoof.cpuElems = &local.cpuElems[offset];
+    spoof.gpuElems = (local.isGpuAccelerated)? &local.gpuElems[offset] : local.gpuElems;
+    return spoof;
+}
+
+static Qureg viewMatrAsStateVec(FullStateDiagMatr matr) {
+    Qureg qureg = qureg_populateNonHeapFields(matr.numQubits, false, matr.isDistributed, matr.isGpuAccelerated, matr.isMultithreaded);
+    qureg.cpuAmps = matr.cpuElems;
+    qureg.gpuAmps = matr.gpuElems;
+    return qureg;
+}
+
+static auto withMatchingDistributions(Qureg qureg, FullStateDiagMatr matr) {
+    if (qureg.isDistributed && !matr.isDistributed)
+        return tuple{qureg, viewLocalMatrAsDistributed(matr, qureg)};
+    if (!qureg.isDistributed && matr.isDistributed) {
+        Qureg spoof = qureg_populateNonHeapFields(qureg.numQubits, qureg.isDensityMatrix, matr.isDistributed, qureg.isGpuAccelerated, matr.isMultithreaded);
+        return tuple{viewLocalAsDistributed(qureg, spoof), matr};
+    }
+    return tuple{qureg, matr};
+}
+
+static Qureg viewBuffersAsLocalStateVec(Qureg densmatr) {
+    assert_localiserGivenDensMatr(densmatr);
+    Qureg spoof = qureg_populateNonHeapFields(densmatr.numQubits, false, false, densmatr.isGpuAccelerated, densmatr.isMultithreaded);
+    spoof.cpuAmps = densmatr.cpuCommBuffer;
+    spoof.gpuAmps = densmatr.gpuCommBuffer;
+    return spoof;
+}
+
+static Qureg makeScratchStateVecFor(Qureg densmatr, bool& memWasAlloc) {
+    memWasAlloc = false;
+    Qureg spoof = viewBuffersAsLocalStateVec(densmatr);
+    if (densmatr.isDistributed)
+        return spoof;                       // every rank holds >= 1 column, so the buffer fits a full statevector
+    memWasAlloc = true;
+    spoof.cpuAmps = cpu_allocArray(spoof.numAmps);
+    assert_localiserSuccessfullyAllocatedTempMemory(spoof.cpuAmps, false);
+    if (spoof.isGpuAccelerated) {
+        spoof.gpuAmps = gpu_allocArray(spoof.numAmps);
+        assert_localiserSuccessfullyAllocatedTempMemory(spoof.gpuAmps, true);
+    }
+    return spoof;
+}
+
+static void freeScratchStateVec(Qureg spoof, bool wasMemAlloc) {
+    if (!wasMemAlloc) return;
+    cpu_deallocArray(spoof.cpuAmps);
+    if (spoof.isGpuAccelerated) gpu_deallocArray(spoof.gpuAmps);
+}
+
+
+/*
+ * EXCHANGE PRIMITIVE (localiser.cpp:448-460)
+ */
+
+static void exchangeWhere(Qureg qureg, int pairRank, vector<int> qubits, vector<int> states) {
+    if (qubits.empty()) {
+        comm_exchangeAmpsToBuffers(qureg, pairRank);       // whole shard, no packing
+        return;
+    }
+    qindex numPacked = accel_statevec_packAmpsIntoBuffer(qureg, qubits, states);
+    comm_exchangeSubBuffers(qureg, numPacked, pairRank);
+}
+
+
+/*
+ * GETTERS (localiser.cpp:469-600)
+ */
+
+qcomp localiser_statevec_getAmp(Qureg qureg, qindex globalInd) {
+    if (!qureg.isDistributed) {
+        qcomp amp;
+        accel_statevec_getAmps_sub(&amp, qureg, globalInd, 1);
+        return amp;
+    }
+    qcomp amp = 0;
+    int sender = util_getRankContainingIndex(qureg, globalInd);
+    if (sender == qureg.rank)
+        accel_statevec_getAmps_sub(&amp, qureg, util_getLocalIndexOfGlobalIndex(qureg, globalInd), 1);
+    comm_broadcastAmp(sender, &amp);
+    return amp;
+}
+
+void localiser_statevec_getAmps(qcomp* outAmps, Qureg qureg, qindex globalStartInd, qindex globalNumAmps) {
+    if (!qureg.isDistributed) {
+        accel_statevec_getAmps_sub(outAmps, qureg, globalStartInd, globalNumAmps);
+        return;
+    }
+    int myRank = comm_getRank();
+    int numNodes = comm_getNumNodes();
+    if (util_areAnyVectorElemsWithinNode(myRank, qureg.numAmpsPerNode, globalStartInd, globalNumAmps)) {
+        auto r = util_getLocalIndRangeOfVectorElemsWithinNode(myRank, qureg.numAmpsPerNode, globalStartInd, globalNumAmps);
+        accel_statevec_getAmps_sub(&outAmps[r.localDuplicStartInd], qureg, r.localDistribStartInd, r.numElems);
+    }
+    vector<qindex> globalRecvInds(numNodes), localSendInds(numNodes), numAmpsPerRank(numNodes, 0);
+    for (int sendRank = 0; sendRank < numNodes; sendRank++) {
+        if (!util_areAnyVectorElemsWithinNode(sendRank, qureg.numAmpsPerNode, globalStartInd, globalNumAmps))
+            continue;
+        auto inds = util_getLocalIndRangeOfVectorElemsWithinNode(sendRank, qureg.numAmpsPerNode, globalStartInd, globalNumAmps);
+        globalRecvInds[sendRank] = inds.localDuplicStartInd;
+        localSendInds [sendRank] = inds.localDistribStartInd;
+        numAmpsPerRank[sendRank] = inds.numElems;
+    }
+    comm_combineSubArrays(outAmps, globalRecvInds, localSendInds, numAmpsPerRank);
+}
+
+void localiser_densmatr_getAmps(qcomp** outAmps, Qureg qureg, qindex startRow, qindex startCol, qindex numRows, qindex numCols) {
+    assert_localiserGivenDensMatr(qureg);
+    vector<vector<qcomp>> tempOut;                          // transposed: one contiguous column per row of temp
+    util_tryAllocMatrix(tempOut, numCols, numRows, error_localiserFailedToAllocTempMemory);
+    for (qindex c = 0; c < numCols; c++)
+        localiser_statevec_getAmps(tempOut[c].data(), qureg, util_getGlobalFlatIndex(qureg, startRow, startCol + c), numRows);
+    for (qindex r = 0; r < numRows; r++)
+        for (qindex c = 0; c < numCols; c++)
+            outAmps[r][c] = tempOut[c][r];
+}
+
+void localiser_fullstatediagmatr_getElems(qcomp* outElems, FullStateDiagMatr matr, qindex globalStartInd, qindex globalNumElems) {
+    localiser_statevec_getAmps(outElems, viewMatrAsStateVec(matr), globalStartInd, globalNumElems);
+}
+
+
+/*
+ * SETTERS (localiser.cpp:607-676)
+ */
+
+void localiser_statevec_setAmps(qcomp* inAmps, Qureg qureg, qindex globalStartInd, qindex globalNumAmps) {
+    if (!qureg.isDistributed) {
+        accel_statevec_setAmps_sub(inAmps, qureg, globalStartInd, globalNumAmps);
+        return;
+    }
+    if (!util_areAnyVectorElemsWithinNode(qureg.rank, qureg.numAmpsPerNode, globalStartInd, globalNumAmps))
+        return;
+    auto range = util_getLocalIndRangeOfVectorElemsWithinNode(qureg.rank, qureg.numAmpsPerNode, globalStartInd, globalNumAmps);
+    accel_statevec_setAmps_sub(&inAmps[range.localDuplicStartInd], qureg, range.localDistribStartInd, range.numElems);
+}
+
+void localiser_densmatr_setAmps(qcomp** inAmps, Qureg qureg, qindex startRow, qindex startCol, qindex numRows, qindex numCols) {
+    assert_localiserGivenDensMatr(qureg);
+    vector<vector<qcomp>> tempAmps;
+    util_tryAllocMatrix(tempAmps, numCols, numRows, error_localiserFailedToAllocTempMemory);
+    for (qindex c = 0; c < numCols; c++)
+        for (qindex r = 0; r < numRows; r++)
+            tempAmps[c][r] = inAmps[r][c];
+    for (qindex c = 0; c < numCols; c++)
+        localiser_statevec_setAmps(tempAmps[c].data(), qureg, util_getGlobalFlatIndex(qureg, startRow, startCol + c), numRows);
+}
+
+void localiser_densmatr_setAmpsToPauliStrSum(Qureg qureg, PauliStrSum sum) {
+    assert_localiserGivenDensMatr(qureg);
+    accel_densmatr_setAmpsToPauliStrSum_sub(qureg, sum);
+}
+
+void localiser_fullstatediagmatr_setElems(FullStateDiagMatr matr, qindex startInd, qcomp* in, qindex numElems) {
+    Qureg spoof = viewMatrAsStateVec(matr);
+    localiser_statevec_setAmps(in, spoof, startInd, numElems);
+    if (spoof.isGpuAccelerated) {                       // matrices keep CPU and GPU copies consistent
+        spoof.isGpuAccelerated = 0;
+        localiser_statevec_setAmps(in, spoof, startInd, numElems);
+    }
+}
+
+void localiser_fullstatediagmatr_setElemsToPauliStrSum(FullStateDiagMatr out, PauliStrSum in) {
+    accel_fullstatediagmatr_setElemsToPauliStrSum(out, in);
+}
+
+
+/*
+ * STATE INITIALISATION (localiser.cpp:689-827)
+ */
+
+static void mixDensityMatrixWithStatevector(qreal outProb, Qureg out, qreal inProb, Qureg in);
+
+void localiser_statevec_initArbitraryPureState(Qureg qureg, qcomp* amps) {
+    assert_localiserGivenStateVec(qureg);
+    localiser_statevec_setAmps(amps, qureg, 0, qureg.numAmps);
+}
+
+void localiser_densmatr_initArbitraryPureState(Qureg qureg, qcomp* amps) {
+    assert_localiserGivenDensMatr(qureg);
+    // |amps><amps| from a serial host-only view of the user's array
+    Qureg spoof = qureg_populateNonHeapFields(qureg.numQubits, 0, 0, 0, 0);
+    spoof.cpuAmps = amps;
+    localiser_densmatr_initPureState(qureg, spoof);
+}
+
+void localiser_densmatr_initArbitraryMixedState(Qureg qureg, qcomp** amps) {
+    qindex dim = powerOf2(qureg.numQubits);
+    localiser_densmatr_setAmps(amps, qureg, 0, 0, dim, dim);
+}
+
+void localiser_statevec_initUniformState(Qureg qureg, qcomp amp) {
+    accel_statevec_initUniformState_sub(qureg, amp);
+}
+
+void localiser_statevec_initDebugState(Qureg qureg) {
+    accel_statevec_initDebugState_sub(qureg);
+}
+
+void localiser_statevec_initClassicalState(Qureg qureg, qindex globalInd) {
+    accel_statevec_initUniformState_sub(qureg, 0);
+    qcomp amp = 1;
+    localiser_statevec_setAmps(&amp, qureg, globalInd, 1);
+}
+
+void localiser_densmatr_initPureState(Qureg qureg, Qureg pure) {
+    assert_localiserGivenDensMatr(qureg);
+    assert_localiserGivenStateVec(pure);
+    mixDensityMatrixWithStatevector(0, qureg, 1, pure);
+}
+
+void localiser_statevec_initUnnormalisedUniformlyRandomPureStateAmps(Qureg qureg) {
+    assert_localiserGivenStateVec(qureg);
+    accel_statevec_initUnnormalisedUniformlyRandomPureStateAmps_sub(qureg);
+}
+
+void localiser_densmatr_initUniformlyRandomPureStateAmps(Qureg qureg) {
+    assert_localiserGivenDensMatr(qureg);
+    bool wasMemAlloc = false;
+    Qureg pure = makeScratchStateVecFor(qureg, wasMemAlloc);
+    initRandomPureState(pure);
+    localiser_densmatr_initPureState(qureg, pure);
+    freeScratchStateVec(pure, wasMemAlloc);
+}
+
+void localiser_densmatr_initMixtureOfUniformlyRandomPureStates(Qureg qureg, qindex numPureStates) {
+    assert_localiserGivenDensMatr(qureg);
+    initBlankState(qureg);
+    bool wasMemAlloc = false;
+    Qureg pure = makeScratchStateVecFor(qureg, wasMemAlloc);
+    for (qindex n = 0; n < numPureStates; n++) {
+        initRandomPureState(pure);
+        mixDensityMatrixWithStatevector(1, qureg, 1./numPureStates, pure);
+    }
+    setQuregToRenormalized(qureg);
+    freeScratchStateVec(pure, wasMemAlloc);
+}
+
+
+/*
+ * SWAPS (localiser.cpp:836-932)
+ */
+
+// prefix <-> prefix: only ranks whose two rank bits differ take part; they trade all ctrl-satisfying amps
+static void swapPrefixWithPrefix(Qureg qureg, vector<int> ctrls, vector<int> ctrlStates, int targ1, int targ2) {
+    if (rankBit(qureg, targ1) == rankBit(qureg, targ2))
+        return;
+    int pairRank = rankWithFlipped(qureg, {targ1, targ2});
+    exchangeWhere(qureg, pairRank, ctrls, ctrlStates);
+    accel_statevec_anyCtrlSwap_subB(qureg, ctrls, ctrlStates);
+}
+
+// prefix <-> suffix: every rank trades the half of its shard whose suffix bit differs from its rank bit
+static void swapPrefixWithSuffix(Qureg qureg, vector<int> ctrls, vector<int> ctrlStates, int suffixTarg, int prefixTarg) {
+    int pairRank = rankWithFlipped(qureg, {prefixTarg});
+    int suffixState = ! rankBit(qureg, prefixTarg);
+
+    // NVLink fast path: swap the two half-shards in place through peer memory, no packing and no buffer
+    if (ctrls.empty() && qureg.isGpuAccelerated && qb_p2p_is_available()) {
+        auto s = toState(qureg);
+        QB_CHECK( qb_p2p_swapHalves(&s, suffixTarg, pairRank) );
+        return;
+    }
+
+    vector<int> qubits = ctrls, states = ctrlStates;
+    qubits.push_back(suffixTarg);
+    states.push_back(suffixState);
+    exchangeWhere(qureg, pairRank, qubits, states);
+    accel_statevec_anyCtrlSwap_subC(qureg, ctrls, ctrlStates, suffixTarg, suffixState);
+}
+
+void localiser_statevec_anyCtrlSwap(Qureg qureg, vector<int> ctrls, vector<int> ctrlStates, int targ1, int targ2) {
+    if (targ1 > targ2)
+        std::swap(targ1, targ2);
+    if (!localiseCtrls(qureg, ctrls, ctrlStates))
+        return;
+    bool pre1 = anyPrefix(qureg, {targ1});
+    bool pre2 = anyPrefix(qureg, {targ2});
+    if (pre2 && pre1)
+        swapPrefixWithPrefix(qureg, ctrls, ctrlStates, targ1, targ2);
+    else if (pre2)
+        swapPrefixWithSuffix(qureg, ctrls, ctrlStates, targ1, targ2);
+    else
+        accel_statevec_anyCtrlSwap_subA(qureg, ctrls, ctrlStates, targ1, targ2);
+}
+
+static void multiSwapPrefixWithSuffix(Qureg qureg, vector<int> targsA, vector<int> targsB) {
+    for (size_t i = 0; i < targsA.size(); i++) {
+        if (targsA[i] == targsB[i])
+            continue;
+        swapPrefixWithSuffix(qureg, {}, {}, std::min(targsA[i], targsB[i]), std::max(targsA[i], targsB[i]));
+    }
+}
+
+
+/*
+ * DENSE MATRICES (localiser.cpp:941-1082)
+ */
+
+void localiser_statevec_anyCtrlOneTargDenseMatr(Qureg qureg, vector<int> ctrls, vector<int> ctrlStates, int targ, CompMatr1 matr, bool conj) {
+    if (!localiseCtrls(qureg, ctrls, ctrlStates))
+        return;
+    if (conj)
+        matr = util_getConj(matr);
+
+    if (!anyPrefix(qureg, {targ})) {
+        accel_statevec_anyCtrlOneTargDenseMatr_subA(qureg, ctrls, ctrlStates, targ, matr);
+        return;
+    }
+
+    int pairRank = rankWithFlipped(qureg, {targ});
+    int bit = rankBit(qureg, targ);
+
+    // NVLink fast path: the pair splits the amplitude pairs between them; each GPU reads/writes the partner's
+    // half over peer memory inside one kernel (half the link traffic of an exchange, no buffer, no combine pass)
+    if (qureg.isGpuAccelerated && qb_p2p_is_available()) {
+        auto s = toState(qureg);
+        QB_CHECK( qb_p2p_anyCtrlOneTargDenseMatr(&s, ctrls.data(), ctrlStates.data(), (int) ctrls.size(), pairRank, bit,
+            reinterpret_cast<const qb_cplx*>(&matr.elems[0][0])) );
+        return;
+    }
+
+    exchangeWhere(qureg, pairRank, ctrls, ctrlStates);
+    qcomp fac0 = matr.elems[bit][ bit];
+    qcomp fac1 = matr.elems[bit][!bit];
+    accel_statevec_anyCtrlOneTargDenseMatr_subB(qureg, ctrls, ctrlStates, fac0, fac1);
+}
+
+static void denseOnSuffix(Qureg qureg, vector<int> ctrls, vector<int> ctrlStates, vector<int> targs, CompMatr2 matr, bool conj) {
+    if (conj) matr = util_getConj(matr);
+    accel_statevec_anyCtrlTwoTargDenseMatr_sub(qureg, ctrls, ctrlStates, targs[0], targs[1], matr);
+}
+
+static void denseOnSuffix(Qureg qureg, vector<int> ctrls, vector<int> ctrlStates, vector<int> targs, CompMatr matr, bool conj) {
+    accel_statevec_anyCtrlAnyTargDenseMatr_sub(qureg, ctrls, ctrlStates, targs, matr, conj);
+}
+
+// finds, for every prefix target, the lowest suffix qubit that is not a target; a control sitting there trades
+// places with the target  [localiser.cpp:146-199 getCtrlsAndTargsSwappedToMinSuffix]
+static tuple<vector<int>,vector<int>> relocateTargetsToSuffix(Qureg qureg, vector<int> ctrls, vector<int> targs) {
+    qindex targMask = getBitMask(targs.data(), targs.size());
+    qindex ctrlMask = getBitMask(ctrls.data(), ctrls.size());
+    int minFree = getIndOfNextRightmostZeroBit(targMask, -1);
+    for (size_t i = 0; i < targs.size(); i++) {
+        int targ = targs[i];
+        if (isSuffix(qureg, targ))
+            continue;
+        if (getBit(ctrlMask, minFree)) {
+            for (int& c : ctrls) if (c == minFree) { c = targ; break; }
+            ctrlMask = flipTwoBits(ctrlMask, minFree, targ);
+        }
+        targs[i] = minFree;
+        targMask = flipTwoBits(targMask, targ, minFree);
+        minFree = getIndOfNextRightmostZeroBit(targMask, minFree);
+    }
+    return {ctrls, targs};
+}
+
+template <typename T>
+static void denseTwoOrMoreTargs(Qureg qureg, vector<int> ctrls, vector<int> ctrlStates, vector<int> targs, T matr, bool conj) {
+    if (!ctrlStates.empty() && ctrlStates.size() != ctrls.size())
+        error_localiserNumCtrlStatesInconsistentWithNumCtrls();
+    if (ctrlStates.empty())
+        ctrlStates.assign(ctrls.size(), 1);
+    if (!prefixValuesMatch(qureg, ctrls, ctrlStates))
+        return;
+
+    if (!anyPrefix(qureg, targs)) {
+        keepSuffix(qureg, ctrls, ctrlStates);
+        denseOnSuffix(qureg, ctrls, ctrlStates, targs, matr, conj);
+        return;
+    }
+
+    // swap prefix targets into the lowest free suffix qubits, apply locally, swap back (localiser.cpp:997-1040)
+    auto [newCtrls, newTargs] = relocateTargetsToSuffix(qureg, ctrls, targs);
+    multiSwapPrefixWithSuffix(qureg, targs, newTargs);
+    if (prefixValuesMatch(qureg, newCtrls, ctrlStates)) {
+        vector<int> c = newCtrls, s = ctrlStates;
+        keepSuffix(qureg, c, s);
+        denseOnSuffix(qureg, c, s, newTargs, matr, conj);
+    }
+    multiSwapPrefixWithSuffix(qureg, targs, newTargs);
+}
+
+void localiser_statevec_anyCtrlTwoTargDenseMatr(Qureg qureg, vector<int> ctrls, vector<int> ctrlStates, int targ1, int targ2, CompMatr2 matr, bool conj) {
+    denseTwoOrMoreTargs(qureg, ctrls, ctrlStates, {targ1, targ2}, matr, conj);
+}
+
+void localiser_statevec_anyCtrlAnyTargDenseMatr(Qureg qureg, vector<int> ctrls, vector<int> ctrlStates, vector<int> targs, CompMatr matr, bool conj) {
+    if (targs.size() == 1)
+        localiser_statevec_anyCtrlOneTargDenseMatr(qureg, ctrls, ctrlStates, targs[0], getCompMatr1(matr.cpuElems), conj);
+    else if (targs.size() == 2)
+        localiser_statevec_anyCtrlTwoTargDenseMatr(qureg, ctrls, ctrlStates, targs[0], targs[1], getCompMatr2(matr.cpuElems), conj);
+    else
+        denseTwoOrMoreTargs(qureg, ctrls, ctrlStates, targs, matr, conj);
+}
+
+
+/*
+ * DIAGONAL MATRICES (localiser.cpp:1089-1207): never communicate; prefix targets read the rank inside the kernel
+ */
+
+void localiser_statevec_anyCtrlOneTargDiagMatr(Qureg qureg, vector<int> ctrls, vector<int> ctrlStates, int targ, DiagMatr1 matr, bool conj) {
+    if (!localiseCtrls(qureg, ctrls, ctrlStates))
+        return;
+    if (conj)
+        matr = util_getConj(matr);
+    accel_statevec_anyCtrlOneTargDiagMatr_sub(qureg, ctrls, ctrlStates, targ, matr);
+}
+
+void localiser_statevec_anyCtrlTwoTargDiagMatr(Qureg qureg, vector<int> ctrls, vector<int> ctrlStates, int targ1, int targ2, DiagMatr2 matr, bool conj) {
+    if (!localiseCtrls(qureg, ctrls, ctrlStates))
+        return;
+    if (conj)
+        matr = util_getConj(matr);
+    accel_statevec_anyCtrlTwoTargDiagMatr_sub(qureg, ctrls, ctrlStates, targ1, targ2, matr);
+}
+
+void localiser_statevec_anyCtrlAnyTargDiagMatr(Qureg qureg, vector<int> ctrls, vector<int> ctrlStates, vector<int> targs, DiagMatr matr, qcomp exponent, bool conj) {
+    if (!localiseCtrls(qureg, ctrls, ctrlStates))
+        return;
+    accel_statevec_anyCtrlAnyTargDiagMatr_sub(qureg, ctrls, ctrlStates, targs, matr, exponent, conj);
+}
+
+void localiser_statevec_allTargDiagMatr(Qureg qureg, FullStateDiagMatr matr, qcomp exponent) {
+    assert_localiserGivenStateVec(qureg);
+    if (!qureg.isDistributed && matr.isDistributed)
+        error_localiserGivenDistribMatrixAndLocalQureg();
+    if (qureg.isDistributed == matr.isDistributed)
+        accel_statevec_allTargDiagMatr_sub(qureg, matr, exponent);
+    else
+        accel_statevec_allTargDiagMatr_sub(qureg, viewLocalMatrAsDistributed(matr, qureg), exponent);
+}
+
+void localiser_densmatr_allTargDiagMatr(Qureg qureg, FullStateDiagMatr matr, qcomp exponent, bool multiplyOnly) {
+    assert_localiserGivenDensMatr(qureg);
+    if (!qureg.isDistributed && matr.isDistributed) {
+        error_localiserGivenDistribMatrixAndLocalQureg();
+        return;
+    }
+    if (!matr.isDistributed) {
+        accel_densmatr_allTargDiagMatr_subA(qureg, matr, exponent, multiplyOnly);
+        return;
+    }
+    comm_combineElemsIntoBuffer(qureg, matr);               // all-gather the diagonal into every rank's buffer
+    accel_densmatr_allTargDiagMatr_subB(qureg, matr, exponent, multiplyOnly);
+}
+
+template <class T>
+void localiser_statevec_anyCtrlAnyTargAnyMatr(Qureg qureg, vector<int> ctrls, vector<int> ctrlStates, vector<int> targs, T matr, bool conj) {
+    if constexpr (util_isDiagMatr <T>()) localiser_statevec_anyCtrlAnyTargDiagMatr(qureg,  ctrls, ctrlStates, targs, matr, 1, conj);
+    if constexpr (util_isDiagMatr1<T>()) localiser_statevec_anyCtrlOneTargDiagMatr(qureg,  ctrls, ctrlStates, targs[0], matr, conj);
+    if constexpr (util_isDiagMatr2<T>()) localiser_statevec_anyCtrlTwoTargDiagMatr(qureg,  ctrls, ctrlStates, targs[0], targs[1], matr, conj);
+    if constexpr (util_isCompMatr <T>()) localiser_statevec_anyCtrlAnyTargDenseMatr(qureg, ctrls, ctrlStates, targs, matr, conj);
+    if constexpr (util_isCompMatr1<T>()) localiser_statevec_anyCtrlOneTargDenseMatr(qureg, ctrls, ctrlStates, targs[0], matr, conj);
+    if constexpr (util_isCompMatr2<T>()) localiser_statevec_anyCtrlTwoTargDenseMatr(qureg, ctrls, ctrlStates, targs[0], targs[1], matr, conj);
+}
+
+template void localiser_statevec_anyCtrlAnyTargAnyMatr(Qureg, vector<int>, vector<int>, vector<int>, DiagMatr,  bool);
+template void localiser_statevec_anyCtrlAnyTargAnyMatr(Qureg, vector<int>, vector<int>, vector<int>, DiagMatr1, bool);
+template void localiser_statevec_anyCtrlAnyTargAnyMatr(Qureg, vector<int>, vector<int>, vector<int>, DiagMatr2, bool);
+template void localiser_statevec_anyCtrlAnyTargAnyMatr(Qureg, vector<int>, vector<int>, vector<int>, CompMatr,  bool);
+template void localiser_statevec_anyCtrlAnyTargAnyMatr(Qureg, vector<int>, vector<int>, vector<int>, CompMatr1, bool);
+template void localiser_statevec_anyCtrlAnyTargAnyMatr(Qureg, vector<int>, vector<int>, vector<int>, CompMatr2, bool);
+
+
+/*
+ * PAULI TENSORS AND GADGETS (localiser.cpp:1247-1360)
+ */
+
+static void zTensorOrGadget(Qureg qureg, vector<int> ctrls, vector<int> ctrlStates, vector<int> targs, bool isGadget, qreal phase) {
+    if (!localiseCtrls(qureg, ctrls, ctrlStates))
+        return;
+    // prefix Z only contribute a rank-wide sign
+    auto [prefixZ, suffixZ] = util_getPrefixAndSuffixQubits(targs, qureg);
+    int sign = paulis_getPrefixZSign(qureg, prefixZ);
+    qcomp fac0 = (isGadget)? std::exp(+ phase * sign * 1_i) : qcomp(+1 * sign, 0);
+    qcomp fac1 = (isGadget)? std::exp(- phase * sign * 1_i) : qcomp(-1 * sign, 0);
+    accel_statevector_anyCtrlAnyTargZOrPhaseGadget_sub(qureg, ctrls, ctrlStates, suffixZ, fac0, fac1);
+}
+
+static void pauliTensorOrGadget(Qureg qureg, vector<int> ctrls, vector<int> ctrlStates, PauliStr str, qcomp ampFac, qcomp pairAmpFac) {
+    if (!paulis_containsXOrY(str))
+        error_localiserGivenPauliStrWithoutXorY();
+    if (!localiseCtrls(qureg, ctrls, ctrlStates))
+        return;
+
+    auto [targsX, targsY, targsZ] = paulis_getSeparateInds(str, qureg);
+    auto [prefixX, suffixX] = util_getPrefixAndSuffixQubits(targsX, qureg);
+    auto [prefixY, suffixY] = util_getPrefixAndSuffixQubits(targsY, qureg);
+    auto [prefixZ, suffixZ] = util_getPrefixAndSuffixQubits(targsZ, qureg);
+
+    // prefix Y and Z fold into one rank-dependent scalar on the partner amplitude
+    pairAmpFac *= paulis_getPrefixPaulisElem(qureg, prefixY, prefixZ);
+
+    if (prefixX.empty() && prefixY.empty()) {
+        accel_statevector_anyCtrlPauliTensorOrGadget_subA(qureg, ctrls, ctrlStates, suffixX, suffixY, suffixZ, ampFac, pairAmpFac);
+        return;
+    }
+
+    // prefix X/Y flip rank bits: the partner amplitudes live on exactly one other rank
+    auto prefixXY = util_getConcatenated(prefixX, prefixY);
+    int pairRank = rankWithFlipped(qureg, prefixXY);
+    exchangeWhere(qureg, pairRank, ctrls, ctrlStates);
+
+    // the received buffer is compacted over the control qubits, so its XY mask drops those bits
+    auto sortedCtrls = util_getSorted(ctrls);
+    auto suffixMaskXY = util_getBitMask(util_getConcatenated(suffixX, suffixY));
+    auto bufferMaskXY = removeBits(suffixMaskXY, sortedCtrls.data(), sortedCtrls.size());
+    accel_statevector_anyCtrlPauliTensorOrGadget_subB(qureg, ctrls, ctrlStates, suffixX, suffixY, suffixZ, ampFac, pairAmpFac, bufferMaskXY);
+}
+
+void localiser_statevec_anyCtrlPauliTensor(Qureg qureg, vector<int> ctrls, vector<int> ctrlStates, PauliStr str, qcomp factor) {
+    if (paulis_containsXOrY(str)) {
+        pauliTensorOrGadget(qureg, ctrls, ctrlStates, str, 0 * factor, 1 * factor);
+    } else {
+        if (factor != qcomp(1,0))
+            error_localiserGivenNonUnityGlobalFactorToZTensor();
+        zTensorOrGadget(qureg, ctrls, ctrlStates, paulis_getInds(str), false, 0);
+    }
+}
+
+void localiser_statevec_anyCtrlPhaseGadget(Qureg qureg, vector<int> ctrls, vector<int> ctrlStates, vector<int> targs, qreal phase) {
+    zTensorOrGadget(qureg, ctrls, ctrlStates, targs, true, phase);
+}
+
+void localiser_statevec_anyCtrlPauliGadget(Qureg qureg, vector<int> ctrls, vector<int> ctrlStates, PauliStr str, qreal phase) {
+    if (!paulis_containsXOrY(str)) {
+        localiser_statevec_anyCtrlPhaseGadget(qureg, ctrls, ctrlStates, paulis_getInds(str), phase);
+        return;
+    }
+    qcomp ampFac     = std::cos(phase);
+    qcomp pairAmpFac = std::sin(phase) * 1_i;
+    pauliTensorOrGadget(qureg, ctrls, ctrlStates, str, ampFac, pairAmpFac);
+}
+
+
+/*
+ * QUREG COMBINATION (localiser.cpp:1369-1420)
+ */
+
+void localiser_statevec_setQuregToSuperposition(qcomp facOut, Qureg outQureg, qcomp fac1, Qureg inQureg1, qcomp fac2, Qureg inQureg2) {
+    accel_statevec_setQuregToSuperposition_sub(facOut, outQureg, fac1, inQureg1, fac2, inQureg2);
+}
+
+static void mixDensityMatrixWithStatevector(qreal outProb, Qureg out, qreal inProb, Qureg in) {
+    bool outDist = out.isDistributed;
+    bool inDist = in.isDistributed;
+    if (!outDist && inDist)
+        error_mixQuregsAreLocalDensMatrAndDistribStatevec();
+    if (!outDist && !inDist)
+        accel_densmatr_mixQureg_subB(outProb, out, inProb, in);
+    if (outDist && inDist) {
+        comm_combineAmpsIntoBuffer(out, in);                // all-gather psi into every rank's buffer
+        accel_densmatr_mixQureg_subC(outProb, out, inProb);
+    }
+    if (outDist && !inDist)
+        accel_densmatr_mixQureg_subD(outProb, out, inProb, in);
+}
+
+void localiser_densmatr_mixQureg(qreal outProb, Qureg out, qreal inProb, Qureg in) {
+    assert_localiserGivenDensMatr(out);
+    (in.isDensityMatrix)?
+        accel_densmatr_mixQureg_subA(outProb, out, inProb, in):
+        mixDensityMatrixWithStatevector(outProb, out, inProb, in);
+}
+
+
+/*
+ * DECOHERENCE (localiser.cpp:1429-1640): ket qubits are always suffix; a channel communicates iff the BRA
+ * qubit (ket + numQubits) is a prefix qubit, and then always with the rank whose bra bit is flipped
+ */
+
+void localiser_densmatr_oneQubitDephasing(Qureg qureg, int qubit, qreal prob) {
+    assert_localiserGivenDensMatr(qureg);
+    (braIsPrefix(qureg, qubit))?
+        accel_densmatr_oneQubitDephasing_subB(qureg, qubit, prob):
+        accel_densmatr_oneQubitDephasing_subA(qureg, qubit, prob);
+}
+
+void localiser_densmatr_twoQubitDephasing(Qureg qureg, int qubit1, int qubit2, qreal prob) {
+    assert_localiserGivenDensMatr(qureg);
+    (braIsPrefix(qureg, std::max(qubit1, qubit2)))?
+        accel_densmatr_twoQubitDephasing_subB(qureg, qubit1, qubit2, prob):
+        accel_densmatr_twoQubitDephasing_subA(qureg, qubit1, qubit2, prob);
+}
+
+void localiser_densmatr_oneQubitDepolarising(Qureg qureg, int qubit, qreal prob) {
+    assert_localiserGivenDensMatr(qureg);
+    if (!braIsPrefix(qureg, qubit)) {
+        accel_densmatr_oneQubitDepolarising_subA(qureg, qubit, prob);
+        return;
+    }
+    int braBit = util_getRankBitOfBraQubit(qubit, qureg);
+    int pairRank = util_getRankWithBraQubitFlipped(qubit, qureg);
+    exchangeWhere(qureg, pairRank, {qubit}, {braBit});      // the |.A.><.A.| half travels
+    accel_densmatr_oneQubitDepolarising_subB(qureg, qubit, prob);
+}
+
+void localiser_densmatr_twoQubitDepolarising(Qureg qureg, int qubit1, int qubit2, qreal prob) {
+    assert_localiserGivenDensMatr(qureg);
+    if (qubit1 > qubit2)
+        std::swap(qubit1, qubit2);
+    bool comm1 = braIsPrefix(qureg, qubit1);
+    bool comm2 = braIsPrefix(qureg, qubit2);
+
+    if (!comm2) {
+        accel_densmatr_twoQubitDepolarising_subA(qureg, qubit1, qubit2, prob);
+        accel_densmatr_twoQubitDepolarising_subB(qureg, qubit1, qubit2, prob);
+        return;
+    }
+
+    if (!comm1) {
+        // bra2 prefix, bra1 suffix: scale, send pair-summed amps (an eighth of the shard), mix
+        accel_densmatr_twoQubitDepolarising_subC(qureg, qubit1, qubit2, prob);
+        int braQb1 = util_getBraQubit(qubit1, qureg);
+        int braBit2 = util_getRankBitOfBraQubit(qubit2, qureg);
+        qindex numPacked = accel_statevec_packPairSummedAmpsIntoBuffer(qureg, qubit1, qubit2, braQb1, braBit2);
+        comm_exchangeSubBuffers(qureg, numPacked, util_getRankWithBraQubitFlipped(qubit2, qureg));
+        accel_densmatr_twoQubitDepolarising_subD(qureg, qubit1, qubit2, prob);
+        return;
+    }
+
+    // both bras prefix: the same packed quarter goes to the three other ranks of the 2x2 rank-bit square
+    int braBit1 = util_getRankBitOfBraQubit(qubit1, qureg);
+    int braBit2 = util_getRankBitOfBraQubit(qubit2, qureg);
+    qindex numPacked = accel_statevec_packAmpsIntoBuffer(qureg, {qubit1, qubit2}, {braBit1, braBit2});
+    accel_densmatr_twoQubitDepolarising_subE(qureg, qubit1, qubit2, prob);
+    int pairRanks[3] = {
+        util_getRankWithBraQubitFlipped(qubit1, qureg),
+        util_getRankWithBraQubitFlipped(qubit2, qureg),
+        util_getRankWithBraQubitsFlipped({qubit1, qubit2}, qureg)};
+    for (int pairRank : pairRanks) {
+        comm_exchangeSubBuffers(qureg, numPacked, pairRank);
+        accel_densmatr_twoQubitDepolarising_subF(qureg, qubit1, qubit2, prob);
+    }
+}
+
+void localiser_densmatr_oneQubitPauliChannel(Qureg qureg, int qubit, qreal probX, qreal probY, qreal probZ) {
+    assert_localiserGivenDensMatr(qureg);
+    qreal probI = 1 - probX - probY - probZ;
+    if (!braIsPrefix(qureg, qubit)) {
+        accel_densmatr_oneQubitPauliChannel_subA(qureg, qubit, probI, probX, probY, probZ);
+        return;
+    }
+    comm_exchangeAmpsToBuffers(qureg, util_getRankWithBraQubitFlipped(qubit, qureg));
+    accel_densmatr_oneQubitPauliChannel_subB(qureg, qubit, probI, probX, probY, probZ);
+}
+
+void localiser_densmatr_oneQubitDamping(Qureg qureg, int qubit, qreal prob) {
+    assert_localiserGivenDensMatr(qureg);
+    if (!braIsPrefix(qureg, qubit)) {
+        accel_densmatr_oneQubitDamping_subA(qureg, qubit, prob);
+        return;
+    }
+    // one-way traffic: ranks with bra bit 1 send their |.1.> half to the bra-bit-0 partner (localiser.cpp:1599-1629)
+    int braBit = util_getRankBitOfBraQubit(qubit, qureg);
+    int pairRank = util_getRankWithBraQubitFlipped(qubit, qureg);
+    qindex numAmps = qureg.numAmpsPerNode / 2;
+    if (braBit == 1) {
+        accel_statevec_packAmpsIntoBuffer(qureg, {qubit}, {1});
+        comm_asynchSendSubBuffer(qureg, numAmps, pairRank);
+        accel_densmatr_oneQubitDamping_subB(qureg, qubit, prob);
+    }
+    accel_densmatr_oneQubitDamping_subC(qureg, qubit, prob);
+    if (braBit == 0) {
+        comm_receiveArrayToBuffer(qureg, numAmps, pairRank);
+        accel_densmatr_oneQubitDamping_subD(qureg, qubit, prob);
+    }
+}
+
+
+/*
+ * SUPEROPERATORS AND KRAUS MAPS (localiser.cpp:1648-1686): a dense matrix on ket + bra targets
+ */
+
+void localiser_densmatr_superoperator(Qureg qureg, SuperOp op, vector<int> ketTargs) {
+    assert_localiserGivenDensMatr(qureg);
+    CompMatr matr;
+    matr.numQubits = 2 * op.numQubits;
+    matr.numRows = op.numRows;
+    matr.isApproxUnitary = nullptr;
+    matr.isApproxHermitian = nullptr;
+    matr.wasGpuSynced = nullptr;
+    matr.cpuElems = op.cpuElems;
+    matr.cpuElemsFlat = op.cpuElemsFlat;
+    matr.gpuElemsFlat = op.gpuElemsFlat;
+    auto allTargs = util_getConcatenated(ketTargs, util_getBraQubits(ketTargs, qureg));
+    localiser_statevec_anyCtrlAnyTargDenseMatr(qureg, {}, {}, allTargs, matr, false);
+}
+
+void localiser_densmatr_krausMap(Qureg qureg, KrausMap map, vector<int> ketTargs) {
+    localiser_densmatr_superoperator(qureg, map.superop, ketTargs);
+}
+
+
+/*
+ * PARTIAL TRACE (localiser.cpp:1695-1812)
+ */
+
+static vector<int> relocateQubitsToTopOfSuffix(Qureg qureg, vector<int> qubits) {     // getQubitsSwappedToMaxSuffix
+    if (!anyPrefix(qureg, qubits))
+        return qubits;
+    qindex qubitMask = getBitMask(qubits.data(), qubits.size());
+    int maxFree = getIndOfNextLeftmostZeroBit(qubitMask, qureg.logNumAmpsPerNode);
+    for (size_t i = qubits.size(); i-- != 0; ) {
+        int qubit = qubits[i];
+        if (isSuffix(qureg, qubit))
+            continue;
+        qubits[i] = maxFree;
+        qubitMask = flipTwoBits(qubitMask, qubit, maxFree);
+        maxFree = getIndOfNextLeftmostZeroBit(qubitMask, maxFree);
+    }
+    return qubits;
+}
+
+static vector<int> orderOfSurvivingQubits(Qureg qureg, vector<int> originalTargs, vector<int> revisedTargs) {   // getNonTracedQubitOrder
+    vector<int> allQubits(2 * qureg.numQubits);
+    for (size_t q = 0; q < allQubits.size(); q++)
+        allQubits[q] = q;
+    for (size_t i = 0; i < originalTargs.size(); i++)
+        if (originalTargs[i] != revisedTargs[i])
+            std::swap(allQubits[originalTargs[i]], allQubits[revisedTargs[i]]);
+    qindex revisedMask = util_getBitMask(revisedTargs);
+    vector<int> remaining;
+    for (size_t q = 0; q < allQubits.size(); q++)
+        if (!getBit(revisedMask, q))
+            remaining.push_back(allQubits[q]);
+    qindex remainingMask = util_getBitMask(remaining);
+    for (int& qubit : remaining) {
+        int bound = qubit;
+        for (int i = 0; i < bound; i++)
+            qubit -= ! getBit(remainingMask, i);
+    }
+    return remaining;
+}
+
+void localiser_densmatr_partialTrace(Qureg inQureg, Qureg outQureg, vector<int> targs) {
+    assert_localiserPartialTraceGivenCompatibleQuregs(inQureg, outQureg, targs.size());
+    auto ketTargs = util_getSorted(targs);
+    auto braTargs = util_getBraQubits(ketTargs, inQureg);
+
+    if (!braIsPrefix(inQureg, ketTargs.back())) {
+        accel_densmatr_partialTrace_sub(inQureg, outQureg, ketTargs, braTargs);
+        return;
+    }
+
+    // prefix bra targets are swapped to the top of the suffix, traced, the survivors re-ordered, swaps undone
+    auto allTargs = util_getSorted(ketTargs, braTargs);
+    auto sufTargs = relocateQubitsToTopOfSuffix(inQureg, allTargs);
+    multiSwapPrefixWithSuffix(inQureg, sufTargs, allTargs);
+    vector<int> pairTargs(sufTargs.begin() + ketTargs.size(), sufTargs.end());
+    accel_densmatr_partialTrace_sub(inQureg, outQureg, ketTargs, pairTargs);
+
+    auto remaining = orderOfSurvivingQubits(inQureg, allTargs, sufTargs);
+    for (int qubit = (int) remaining.size(); qubit-- != 0; ) {
+        if (remaining[qubit] == qubit)
+            continue;
+        int pair = 0;
+        while (remaining[pair] != qubit)
+            pair++;
+        localiser_statevec_anyCtrlSwap(outQureg, {}, {}, qubit, pair);
+        std::swap(remaining[qubit], remaining[pair]);
+    }
+    multiSwapPrefixWithSuffix(inQureg, sufTargs, allTargs);
+}
+
+
+/*
+ * PROBABILITIES (localiser.cpp:1821-1951): local reduction, then a sum over ranks
+ */
+
+qreal localiser_statevec_calcTotalProb(Qureg qureg) {
+    qreal prob = accel_statevec_calcTotalProb_sub(qureg);
+    if (qureg.isDistributed)
+        comm_reduceReal(&prob);
+    return prob;
+}
+
+qreal localiser_densmatr_calcTotalProb(Qureg qureg) {
+    assert_localiserGivenDensMatr(qureg);
+    qreal prob = accel_densmatr_calcTotalProb_sub(qureg);
+    if (qureg.isDistributed)
+        comm_reduceReal(&prob);
+    return prob;
+}
+
+qreal localiser_statevec_calcProbOfMultiQubitOutcome(Qureg qureg, vector<int> qubits, vector<int> outcomes) {
+    assert_localiserGivenStateVec(qureg);
+    qreal prob = 0;
+    if (prefixValuesMatch(qureg, qubits, outcomes)) {
+        if (qureg.isDistributed)
+            keepSuffix(qureg, qubits, outcomes);
+        prob += accel_statevec_calcProbOfMultiQubitOutcome_sub(qureg, qubits, outcomes);
+    }
+    if (qureg.isDistributed)
+        comm_reduceReal(&prob);
+    return prob;
+}
+
+qreal localiser_densmatr_calcProbOfMultiQubitOutcome(Qureg qureg, vector<int> qubits, vector<int> outcomes) {
+    assert_localiserGivenDensMatr(qureg);
+    qreal prob = 0;
+    auto braQubits = util_getBraQubits(qubits, qureg);
+    if (prefixValuesMatch(qureg, braQubits, outcomes)) {
+        vector<int> kets, outs;
+        for (size_t q = 0; q < qubits.size(); q++)
+            if (!braIsPrefix(qureg, qubits[q])) {
+                kets.push_back(qubits[q]);
+                outs.push_back(outcomes[q]);
+            }
+        prob += accel_densmatr_calcProbOfMultiQubitOutcome_sub(qureg, kets, outs);
+    }
+    if (qureg.isDistributed)
+        comm_reduceReal(&prob);
+    return prob;
+}
+
+void localiser_statevec_calcProbsOfAllMultiQubitOutcomes(qreal* outProbs, Qureg qureg, vector<int> qubits) {
+    assert_localiserGivenStateVec(qureg);
+    accel_statevec_calcProbsOfAllMultiQubitOutcomes_sub(outProbs, qureg, qubits);
+    if (qureg.isDistributed)
+        comm_reduceReals(outProbs, powerOf2(qubits.size()));
+}
+
+void localiser_densmatr_calcProbsOfAllMultiQubitOutcomes(qreal* outProbs, Qureg qureg, vector<int> qubits) {
+    assert_localiserGivenDensMatr(qureg);
+    accel_densmatr_calcProbsOfAllMultiQubitOutcomes_sub(outProbs, qureg, qubits);
+    if (qureg.isDistributed)
+        comm_reduceReals(outProbs, powerOf2(qubits.size()));
+}
+
+
+/*
+ * EXPECTATION VALUES (localiser.cpp:1963-2186)
+ */
+
+static qcomp expecSuffixPauliStr(Qureg qureg, vector<int> x, vector<int> y, vector<int> z) {
+    if (x.empty() && y.empty() && z.empty())
+        return accel_statevec_calcTotalProb_sub(qureg);
+    if (x.empty() && y.empty())
+        return accel_statevec_calcExpecAnyTargZ_sub(qureg, z);
+    return accel_statevec_calcExpecPauliStr_subA(qureg, x, y, z);
+}
+
+static qcomp expecDensMatrPauliStrLocal(Qureg qureg, PauliStr str) {
+    auto [x, y, z] = paulis_getSeparateInds(str, qureg);
+    if (x.empty() && y.empty() && z.empty())
+        return accel_densmatr_calcTotalProb_sub(qureg);
+    if (x.empty() && y.empty())
+        return accel_densmatr_calcExpecAnyTargZ_sub(qureg, z);
+    return accel_densmatr_calcExpecPauliStr_sub(qureg, x, y, z);
+}
+
+qcomp localiser_statevec_calcExpecPauliStr(Qureg qureg, PauliStr str) {
+    assert_localiserGivenStateVec(qureg);
+    auto [targsX, targsY, targsZ] = paulis_getSeparateInds(str, qureg);
+    auto [prefixX, suffixX] = util_getPrefixAndSuffixQubits(targsX, qureg);
+    auto [prefixY, suffixY] = util_getPrefixAndSuffixQubits(targsY, qureg);
+    auto [prefixZ, suffixZ] = util_getPrefixAndSuffixQubits(targsZ, qureg);
+
+    qcomp value;
+    if (prefixX.empty() && prefixY.empty()) {
+        value = expecSuffixPauliStr(qureg, suffixX, suffixY, suffixZ);
+    } else {
+        comm_exchangeAmpsToBuffers(qureg, rankWithFlipped(qureg, util_getConcatenated(prefixX, prefixY)));
+        value = accel_statevec_calcExpecPauliStr_subB(qureg, suffixX, suffixY, suffixZ);
+    }
+    value *= paulis_getPrefixPaulisElem(qureg, prefixY, prefixZ);
+    if (qureg.isDistributed)
+        comm_reduceAmp(&value);
+    return value;
+}
+
+qcomp localiser_densmatr_calcExpecPauliStr(Qureg qureg, PauliStr str) {
+    assert_localiserGivenDensMatr(qureg);
+    qcomp value = expecDensMatrPauliStrLocal(qureg, str);
+    if (qureg.isDistributed)
+        comm_reduceAmp(&value);
+    return value;
+}
+
+qcomp localiser_statevec_calcExpecPauliStrSum(Qureg qureg, PauliStrSum sum) {
+    assert_localiserGivenStateVec(qureg);
+
+    // terms whose PREFIX X/Y pattern coincides need the same partner rank: one exchange serves the whole group
+    // (localiser.cpp:2052-2125).  std::map keeps the group order deterministic and identical on every rank.
+    std::map<PAULI_MASK_TYPE, vector<qindex>> groups;
+    for (qindex i = 0; i < sum.numTerms; i++) {
+        PAULI_MASK_TYPE totalKey = paulis_getKeyOfSameMixedAmpsGroup(sum.strings[i]);
+        PAULI_MASK_TYPE prefixKey = getBitsLeftOfIndex(totalKey, qureg.logNumAmpsPerNode - 1);
+        groups[prefixKey].push_back(i);
+    }
+
+    qcomp totalValue = 0;
+    for (auto& [key, termInds] : groups) {
+        int pairRank = flipBits(qureg.rank, key);
+        bool remote = pairRank != qureg.rank;
+        if (remote)
+            comm_exchangeAmpsToBuffers(qureg, pairRank);
+
+        vector<qcomp> factors(termInds.size());
+        vector<unsigned long long> masks(2 * termInds.size());
+        vector<int> numY(termInds.size());
+        vector<std::array<vector<int>,3>> suffixes(termInds.size());
+        for (size_t t = 0; t < termInds.size(); t++) {
+            auto [targsX, targsY, targsZ] = paulis_getSeparateInds(sum.strings[termInds[t]], qureg);
+            auto [prefixX, suffixX] = util_getPrefixAndSuffixQubits(targsX, qureg);
+            auto [prefixY, suffixY] = util_getPrefixAndSuffixQubits(targsY, qureg);
+            auto [prefixZ, suffixZ] = util_getPrefixAndSuffixQubits(targsZ, qureg);
+            (void) prefixX;
+            factors[t] = paulis_getPrefixPaulisElem(qureg, prefixY, prefixZ);
+            masks[2*t]   = util_getBitMask(util_getConcatenated(suffixX, suffixY));
+            masks[2*t+1] = util_getBitMask(util_getConcatenated(suffixY, suffixZ));
+            numY[t] = (int) suffixY.size();
+            suffixes[t] = {suffixX, suffixY, suffixZ};
+        }
+
+        if (qureg.isGpuAccelerated) {
+            // fused: every term of the group in batches sharing one pass over the shard
+            vector<qb_cplx> raw(termInds.size());
+            auto s = toState(qureg);
+            QB_CHECK( (remote)?
+                qb_statevec_calcExpecPauliStrBatch_subB(&s, masks.data(), (int) termInds.size(), raw.data()):
+                qb_statevec_calcExpecPauliStrBatch_subA(&s, masks.data(), (int) termInds.size(), raw.data()) );
+            for (size_t t = 0; t < termInds.size(); t++) {
+                qcomp termValue = qcomp(raw[t].re, raw[t].im) * util_getPowerOfI(numY[t]);
+                totalValue += sum.coeffs[termInds[t]] * factors[t] * termValue;
+            }
+        } else {
+            for (size_t t = 0; t < termInds.size(); t++) {
+                auto& [x, y, z] = suffixes[t];
+                qcomp termValue = (remote)? accel_statevec_calcExpecPauliStr_subB(qureg, x, y, z) : expecSuffixPauliStr(qureg, x, y, z);
+                totalValue += sum.coeffs[termInds[t]] * factors[t] * termValue;
+            }
+        }
+    }
+
+    if (qureg.isDistributed)
+        comm_reduceAmp(&totalValue);
+    return totalValue;
+}
+
+qcomp localiser_densmatr_calcExpecPauliStrSum(Qureg qureg, PauliStrSum sum) {
+    assert_localiserGivenDensMatr(qureg);
+    qcomp value = 0;
+    for (qindex t = 0; t < sum.numTerms; t++)
+        value += sum.coeffs[t] * expecDensMatrPauliStrLocal(qureg, sum.strings[t]);
+    if (qureg.isDistributed)
+        comm_reduceAmp(&value);
+    return value;
+}
+
+qcomp localiser_statevec_calcExpecFullStateDiagMatr(Qureg qureg, FullStateDiagMatr matr, qcomp exponent, bool useRealPow) {
+    auto [quregSpoof, matrSpoof] = withMatchingDistributions(qureg, matr);
+    qcomp value = accel_statevec_calcExpecFullStateDiagMatr_sub(quregSpoof, matrSpoof, exponent, useRealPow);
+    if (quregSpoof.isDistributed)
+        comm_reduceAmp(&value);
+    return value;
+}
+
+qcomp localiser_densmatr_calcExpecFullStateDiagMatr(Qureg qureg, FullStateDiagMatr matr, qcomp exponent, bool useRealPow) {
+    auto [quregSpoof, matrSpoof] = withMatchingDistributions(qureg, matr);
+    qcomp value = accel_densmatr_calcExpecFullStateDiagMatr_sub(quregSpoof, matrSpoof, exponent, useRealPow);
+    if (quregSpoof.isDistributed)
+        comm_reduceAmp(&value);
+    return value;
+}
+
+
+/*
+ * INNER PRODUCTS (localiser.cpp:2193-2286)
+ */
+
+qcomp localiser_statevec_calcInnerProduct(Qureg quregA, Qureg quregB) {
+    Qureg a = quregA, b = quregB;
+    if (quregA.isDistributed != quregB.isDistributed) {
+        a = (quregA.isDistributed)? quregA : viewLocalAsDistributed(quregA, quregB);
+        b = (quregB.isDistributed)? quregB : viewLocalAsDistributed(quregB, quregA);
+    }
+    qcomp prod = accel_statevec_calcInnerProduct_sub(a, b);
+    if (a.isDistributed)
+        comm_reduceAmp(&prod);
+    return prod;
+}
+
+qcomp localiser_densmatr_calcFidelityWithPureState(Qureg rho, Qureg psi, bool conj) {
+    assert_localiserGivenDensMatr(rho);
+    assert_localiserGivenStateVec(psi);
+    qcomp fid = 0;
+    if (!psi.isDistributed) {
+        fid = accel_densmatr_calcFidelityWithPureState_sub(rho, psi, conj);
+    } else if (!rho.isDistributed) {
+        error_calcFidStateVecDistribWhileDensMatrLocal();
+    } else {
+        comm_combineAmpsIntoBuffer(rho, psi);
+        fid = accel_densmatr_calcFidelityWithPureState_sub(rho, viewBuffersAsLocalStateVec(rho), conj);
+    }
+    if (rho.isDistributed)
+        comm_reduceAmp(&fid);
+    return fid;
+}
+
+qreal localiser_densmatr_calcHilbertSchmidtDistance(Qureg quregA, Qureg quregB) {
+    assert_localiserGivenDensMatr(quregA);
+    assert_localiserGivenDensMatr(quregB);
+    Qureg a = quregA, b = quregB;
+    if (quregA.isDistributed != quregB.isDistributed) {
+        a = (quregA.isDistributed)? quregA : viewLocalAsDistributed(quregA, quregB);
+        b = (quregB.isDistributed)? quregB : viewLocalAsDistributed(quregB, quregA);
+    }
+    qreal dist = accel_densmatr_calcHilbertSchmidtDistance_sub(a, b);
+    if (quregA.isDistributed || quregB.isDistributed)
+        comm_reduceReal(&dist);
+    return dist;
+}
+
+
+/*
+ * PROJECTORS (localiser.cpp:2295-2322)
+ */
+
+void localiser_statevec_multiQubitProjector(Qureg qureg, vector<int> qubits, vector<int> outcomes, qreal prob) {
+    assert_localiserGivenStateVec(qureg);
+    if (!prefixValuesMatch(qureg, qubits, outcomes)) {
+        accel_statevec_initUniformState_sub(qureg, 0);     // this rank's prefix bits contradict the outcome
+        return;
+    }
+    if (qureg.isDistributed)
+        keepSuffix(qureg, qubits, outcomes);
+    (qubits.empty())?
+        accel_statevec_setQuregToSuperposition_sub(1/std::sqrt(prob), qureg, 0, qureg, 0, qureg):
+        accel_statevec_multiQubitProjector_sub(qureg, qubits, outcomes, prob);
+}
+
+void localiser_densmatr_multiQubitProjector(Qureg qureg, vector<int> qubits, vector<int> outcomes, qreal prob) {
+    assert_localiserGivenDensMatr(qureg);
+    accel_densmatr_multiQubitProjector_sub(qureg, qubits, outcomes, prob);
+}

@@ -18,6 +18,14 @@ def main():
     if which == "ref":
         Q = qa.QuEST(qa.REF_LIB)
         Q.initCustomQuESTEnv(0, 0, 1)            # reference: CPU + OpenMP, the parity oracle
+    elif which == "b200dist":
+        # one process per GPU (RANK / WORLD_SIZE / LOCAL_RANK from the launcher); every Qureg is sharded
+        Q = qa.QuEST(qa.B200_LIB)
+        if os.environ.get("QUEST_B200_P2P", "1") == "0":
+            import ctypes
+            ctypes.CDLL(os.path.join(os.path.dirname(qa.B200_LIB), "libquest_b200.so"), mode=ctypes.RTLD_GLOBAL).qb_p2p_set_enabled(0)
+        Q.initCustomQuESTEnv(1, 1, 0)
+        dst = dst + "." + os.environ.get("RANK", "0")
     else:
         Q = qa.QuEST(qa.B200_LIB)
         Q.initCustomQuESTEnv(0, 1, 0)            # product: GPU only; fails loudly without a device
@@ -27,7 +35,7 @@ def main():
             # small Quregs are auto-deployed to the CPU (core/autodeployer.hpp:17-21); the product under test
             # is the GPU backend, so force GPU acceleration exactly as createCustomQureg allows a user to
             for spec in p["quregs"].values():
-                spec.setdefault("custom", [0, 1, 0])
+                spec.setdefault("custom", [1 if which == "b200dist" else 0, 1, 0])
         out = run_program(Q, p)
         if which != "ref":
             for name, inf in out["info"].items():

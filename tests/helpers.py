@@ -65,3 +65,54 @@ def assert_outputs_match(got, want, tol=TOL, label="", int_exact_ops=()):
 
 def load_golden(name):
     return pickle.load(open(os.path.join(GOLDEN_DIR, name), "rb"))
+
+
+def num_gpus():
+    try:
+        import torch
+        return torch.cuda.device_count()
+    except Exception:
+        return 0
+
+
+def run_programs_distributed(progs, world, timeout=1800, env=None, port=29731):
+    """run the programs on `world` GPUs, one worker process per GPU (the launcher model of the backend:
+    RANK / WORLD_SIZE / LOCAL_RANK / MASTER_PORT in the environment, like torchrun).  Returns rank 0's outputs
+    with every density-matrix / distributed dump re-assembled from the per-rank shards (rank r holds the
+    global indices [r*N, (r+1)*N), api/qureg.cpp:42-74)."""
+    with tempfile.TemporaryDirectory() as d:
+        src, dst = os.path.join(d, "in.pkl"), os.path.join(d, "out.pkl")
+        pickle.dump(progs, open(src, "wb"))
+        procs = []
+        for r in range(world):
+            e = dict(os.environ)
+            e.update(env or {})
+            e.update(RANK=str(r), WORLD_SIZE=str(world), LOCAL_RANK=str(r), MASTER_ADDR="127.0.0.1", MASTER_PORT=str(port),
+                     QUEST_B200_ID_FILE=os.path.join(d, "nccl_id"))
+            procs.append(subprocess.Popen([sys.executable, os.path.join(ROOT, "tests", "_worker.py"), "b200dist", src, dst],
+                                          stdout=subprocess.PIPE, stderr=subprocess.PIPE, text=True, env=e))
+        outs, fails = [], []
+        for r, p in enumerate(procs):
+            try:
+                so, se = p.communicate(timeout=timeout)
+            except subprocess.TimeoutExpired:
+                for q in procs:
+                    q.kill()
+                raise RuntimeError(f"distributed worker {r} timed out")
+            if p.returncode != 0:
+                fails.append(f"rank {r} rc={p.returncode}\n{so[-2000:]}\n{se[-3000:]}")
+        if fails:
+            raise RuntimeError("distributed workers failed:\n" + "\n".join(fails))
+        per_rank = [pickle.load(open(f"{dst}.{r}", "rb")) for r in range(world)]
+    merged = per_rank[0]
+    for k, out in enumerate(merged):
+        for name in list(out["dumps"]):
+            info = out["info"][name]
+            if info["isDistributed"] and out["dumps"][name].size == info["numAmpsPerNode"]:
+                out["dumps"][name] = np.concatenate([per_rank[r][k]["dumps"][name] for r in range(world)])
+        # every rank must have computed identical scalars (they are all-reduced)
+        for r in range(1, world):
+            for a, b in zip(out["results"], per_rank[r][k]["results"]):
+                fa, fb = flatten_result(a), flatten_result(b)
+                assert (fa is None and fb is None) or np.array_equal(fa, fb), f"rank {r} disagrees with rank 0: {a} vs {b}"
+    return merged

@@ -1,0 +1,53 @@
+"""Multi-GPU parity: the SAME programs on P GPUs (one process per GPU, state sharded on the top
+log2 P qubits, NCCL / NVLink peer memory for the exchanges) against the single-process reference CPU library.
+With n-qubit states over P ranks only n - log2 P qubits are local, so small n makes nearly every gate hit the
+prefix paths -- the same trick the reference's CI uses (16 ranks on 6-qubit states)."""
+import os
+
+import numpy as np
+import pytest
+
+pytestmark = pytest.mark.gpu
+
+from tests import helpers as H       # noqa: E402
+from tests import programs as P      # noqa: E402
+
+WORLDS = [w for w in (2, 4, 8) if w <= H.num_gpus()]
+
+
+def _measure_ops(prog):
+    return {i for i, op in enumerate(prog["ops"]) if "Measurement" in op[0] and "Forced" not in op[0]}
+
+
+def _check(progs, world, env=None):
+    if not os.path.exists(H.REF_LIB):
+        pytest.skip("oracle/_ref/libQuEST.so not present")
+    want = H.run_programs("ref", progs)
+    got = H.run_programs_distributed(progs, world, env=env)
+    for k, (prog, g, w) in enumerate(zip(progs, got, want)):
+        H.assert_outputs_match(g, w, label=f"P={world} prog[{k}]", int_exact_ops=_measure_ops(prog))
+
+
+@pytest.mark.skipif(not WORLDS, reason="needs >= 2 GPUs")
+@pytest.mark.parametrize("world", WORLDS)
+@pytest.mark.parametrize("p2p", ["1", "0"], ids=["nvlink-p2p", "nccl-only"])
+def test_statevector_gates_sharded(world, p2p):
+    logp = world.bit_length() - 1
+    _check([P.gates_program(logp + 4, 6001, max_ctrls=2), P.gates_program(logp + 7, 6002, num_rounds=1),
+            P.cfg1_program(logp + 8, 6003, 120), P.cfg2_program(logp + 6, 6004, 60)], world, env={"QUEST_B200_P2P": p2p})
+
+
+@pytest.mark.skipif(not WORLDS, reason="needs >= 2 GPUs")
+@pytest.mark.parametrize("world", WORLDS)
+def test_calcs_measurement_sharded(world):
+    logp = world.bit_length() - 1
+    _check([P.calcs_program_sv(logp + 5, 6101), P.measurement_program(logp + 5, 6102), P.cfg5_program(logp + 6, 6103, num_terms=30),
+            P.big_dense_program(logp + 7, 6104, 4), P.big_dense_program(logp + 8, 6105, 6, nc=0)], world)
+
+
+@pytest.mark.skipif(not WORLDS, reason="needs >= 2 GPUs")
+@pytest.mark.parametrize("world", WORLDS)
+def test_density_matrix_sharded(world):
+    logp = world.bit_length() - 1
+    n = max(logp + 1, 4)
+    _check([P.gates_program(n, 6201, dm=1, num_rounds=1, max_ctrls=1), P.channels_program_dm(n, 6202), P.cfg4_program(n + 1, 6203, layers=2)], world)
