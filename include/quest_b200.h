@@ -67,6 +67,7 @@ int         qb_supports_mem_pools(void);                 /* gpu_doesGpuSupportMe
 qb_index    qb_max_concurrent_threads(void);             /* gpu_getMaxNumConcurrentThreads :269 */
 int         qb_device_uuid(char out16[16]);              /* getBoundGpuUuid            gpu_config.cpp:298 */
 int         qb_sync(void);                               /* gpu_sync                   gpu_config.cpp:382 */
+int         qb_flush(void);                              /* launch every deferred gate now (no host wait); implied by every non-gate entry point */
 void*       qb_get_stream(void);                         /* cudaStream_t all compute is issued on */
 int         qb_set_stream(void* cudaStream);
 qb_cplx*    qb_alloc(qb_index numAmps, int* status);     /* gpu_allocArray :399 (NULL + status 0 on OOM)  */

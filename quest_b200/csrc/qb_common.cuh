@@ -43,7 +43,12 @@ int  qb_ensure_ready();   // binds device 0 lazily, allocates scratch; returns 0
 
 #define QB_CUDA(call) do { cudaError_t e__ = (call); if (e__ != cudaSuccess) \
     return qb_set_error((int)e__, #call, __FILE__, __LINE__); } while (0)
-#define QB_READY() do { int r__ = qb_ensure_ready(); if (r__) return r__; } while (0)
+int  qb_flush_internal();  // qb_tile.cu: run every deferred (queued) gate now
+// every entry point first makes the device ready and drains the deferred-gate queue; the fusable gate entry points
+// use QB_READY_NOFLUSH and either append to the queue or flush explicitly before running a direct kernel
+#define QB_READY_NOFLUSH() do { int r__ = qb_ensure_ready(); if (r__) return r__; } while (0)
+#define QB_FLUSH() do { int r__ = qb_flush_internal(); if (r__) return r__; } while (0)
+#define QB_READY() do { QB_READY_NOFLUSH(); QB_FLUSH(); } while (0)
 #define QB_LAUNCH_CHECK() do { g_qb.launches++; cudaError_t e__ = cudaGetLastError(); if (e__ != cudaSuccess) \
     return qb_set_error((int)e__, "kernel launch", __FILE__, __LINE__); } while (0)
 #define QB_REQUIRE(cond, msg) do { if (!(cond)) return qb_set_error(-1, msg, __FILE__, __LINE__); } while (0)

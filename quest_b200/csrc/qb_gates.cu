@@ -358,6 +358,14 @@ static int qb_denseK(const qb_state* q, const BitIns& ins, const BitList& targs,
     return 0;
 }
 
+// direct Pauli pair kernel from raw masks; pairFac already carries i^numY
+int qb_pauli_raw(const qb_state* q, const int* ctrls, const int* cs, int nc, unsigned long long maskXY, unsigned long long maskYZ, qb_cplx ampFac, qb_cplx pairFac) {
+    int high = 63 - __builtin_clzll(maskXY), zero = 0;
+    OpPauliA op; op.ins = qb_make_ins(ctrls, cs, nc, &high, &zero, 1);
+    op.maskXY = (qindex)maskXY; op.maskYZ = (qindex)maskYZ; op.ampFac = mk(ampFac); op.pairFac = mk(pairFac);
+    return qb_launch_tuple((cplx*)q->amps, q->numAmpsPerNode >> (1 + nc), op);
+}
+
 // ------------------------------------------------------------------------------------------
 // C ABI
 // ------------------------------------------------------------------------------------------
@@ -387,10 +395,11 @@ int qb_statevec_packPairSummedAmpsIntoBuffer(const qb_state* q, int q1, int q2, 
 }
 
 int qb_statevec_anyCtrlSwap_subA(const qb_state* q, const int* ctrls, const int* cs, int nc, int t1, int t2) {
-    QB_READY(); QB_CHECK_STATE(q); QB_CHECK_SUFFIX(ctrls, nc, q);
+    QB_READY_NOFLUSH(); QB_CHECK_STATE(q); QB_CHECK_SUFFIX(ctrls, nc, q);
     int ts[2] = {t2, t1}, tst[2] = {0, 1};
     QB_CHECK_SUFFIX(ts, 2, q); QB_REQUIRE(t1 != t2, "swap: identical targets");
     if (qb_tile_try_swap(q, ctrls, cs, nc, t1, t2)) return qb_tile_status();
+    QB_FLUSH();
     OpSwapA op; op.ins = qb_make_ins(ctrls, cs, nc, ts, tst, 2); op.flip = pow2(t1) | pow2(t2);
     return qb_launch_tuple((cplx*)q->amps, q->numAmpsPerNode >> (2 + nc), op);
 }
@@ -410,8 +419,9 @@ int qb_statevec_anyCtrlSwap_subC(const qb_state* q, const int* ctrls, const int*
 }
 
 int qb_statevec_anyCtrlOneTargDenseMatr_subA(const qb_state* q, const int* ctrls, const int* cs, int nc, int targ, const qb_cplx m[4]) {
-    QB_READY(); QB_CHECK_STATE(q); QB_CHECK_SUFFIX(ctrls, nc, q); QB_CHECK_SUFFIX(&targ, 1, q);
+    QB_READY_NOFLUSH(); QB_CHECK_STATE(q); QB_CHECK_SUFFIX(ctrls, nc, q); QB_CHECK_SUFFIX(&targ, 1, q);
     if (qb_tile_try_dense(q, ctrls, cs, nc, &targ, 1, m)) return qb_tile_status();
+    QB_FLUSH();
     int zero = 0;
     OpDense1 op; op.ins = qb_make_ins(ctrls, cs, nc, &targ, &zero, 1); op.tbit = pow2(targ);
     op.m00 = mk(m[0]); op.m01 = mk(m[1]); op.m10 = mk(m[2]); op.m11 = mk(m[3]);
@@ -427,10 +437,11 @@ int qb_statevec_anyCtrlOneTargDenseMatr_subB(const qb_state* q, const int* ctrls
 }
 
 int qb_statevec_anyCtrlTwoTargDenseMatr_sub(const qb_state* q, const int* ctrls, const int* cs, int nc, int t1, int t2, const qb_cplx m[16]) {
-    QB_READY(); QB_CHECK_STATE(q); QB_CHECK_SUFFIX(ctrls, nc, q);
+    QB_READY_NOFLUSH(); QB_CHECK_STATE(q); QB_CHECK_SUFFIX(ctrls, nc, q);
     int ts[2] = {t1, t2}, z[2] = {0, 0};
     QB_CHECK_SUFFIX(ts, 2, q); QB_REQUIRE(t1 != t2, "dense2: identical targets");
     if (qb_tile_try_dense(q, ctrls, cs, nc, ts, 2, m)) return qb_tile_status();
+    QB_FLUSH();
     OpDense2 op; op.ins = qb_make_ins(ctrls, cs, nc, ts, z, 2); op.b1 = pow2(t1); op.b2 = pow2(t2);
     for (int i = 0; i < 16; i++) op.m[i] = mk(m[i]);
     return qb_launch_tuple((cplx*)q->amps, q->numAmpsPerNode >> (2 + nc), op);
@@ -449,18 +460,20 @@ int qb_statevec_anyCtrlAnyTargDenseMatr_sub(const qb_state* q, const int* ctrls,
 }
 
 int qb_statevec_anyCtrlOneTargDiagMatr_sub(const qb_state* q, const int* ctrls, const int* cs, int nc, int targ, const qb_cplx e[2]) {
-    QB_READY(); QB_CHECK_STATE(q); QB_CHECK_SUFFIX(ctrls, nc, q); QB_CHECK_GLOBAL(&targ, 1);
+    QB_READY_NOFLUSH(); QB_CHECK_STATE(q); QB_CHECK_SUFFIX(ctrls, nc, q); QB_CHECK_GLOBAL(&targ, 1);
     if (qb_tile_try_diag(q, ctrls, cs, nc, &targ, 1, e)) return qb_tile_status();
+    QB_FLUSH();
     OpDiag1 op; op.ins = qb_make_ins(ctrls, cs, nc, nullptr, nullptr, 0);
     op.rankBits = (qindex)q->rank << q->logNumAmpsPerNode; op.targ = targ; op.e0 = mk(e[0]); op.e1 = mk(e[1]);
     return qb_launch_map((cplx*)q->amps, q->numAmpsPerNode >> nc, op);
 }
 
 int qb_statevec_anyCtrlTwoTargDiagMatr_sub(const qb_state* q, const int* ctrls, const int* cs, int nc, int t1, int t2, const qb_cplx e[4]) {
-    QB_READY(); QB_CHECK_STATE(q); QB_CHECK_SUFFIX(ctrls, nc, q);
+    QB_READY_NOFLUSH(); QB_CHECK_STATE(q); QB_CHECK_SUFFIX(ctrls, nc, q);
     int ts[2] = {t1, t2};
     QB_CHECK_GLOBAL(ts, 2);
     if (qb_tile_try_diag(q, ctrls, cs, nc, ts, 2, e)) return qb_tile_status();
+    QB_FLUSH();
     OpDiag2 op; op.ins = qb_make_ins(ctrls, cs, nc, nullptr, nullptr, 0);
     op.rankBits = (qindex)q->rank << q->logNumAmpsPerNode; op.t1 = t1; op.t2 = t2;
     for (int i = 0; i < 4; i++) op.e[i] = mk(e[i]);
@@ -496,17 +509,16 @@ static cplx powerOfI(int n) {           // util_getPowerOfI, core/utilities.cpp
 
 int qb_statevector_anyCtrlPauliTensorOrGadget_subA(const qb_state* q, const int* ctrls, const int* cs, int nc,
         const int* x, int nx, const int* y, int ny, const int* z, int nz, qb_cplx ampFac, qb_cplx pairAmpFac) {
-    QB_READY(); QB_CHECK_STATE(q); QB_CHECK_SUFFIX(ctrls, nc, q);
+    QB_READY_NOFLUSH(); QB_CHECK_STATE(q); QB_CHECK_SUFFIX(ctrls, nc, q);
     QB_CHECK_SUFFIX(x, nx, q); QB_CHECK_SUFFIX(y, ny, q); QB_CHECK_SUFFIX(z, nz, q);
     QB_REQUIRE(nx + ny >= 1, "pauli subA: needs at least one X or Y target");
     unsigned long long maskXY = qb_make_mask(x, nx) | qb_make_mask(y, ny);
     unsigned long long maskYZ = qb_make_mask(y, ny) | qb_make_mask(z, nz);
     cplx pf = cmul(mk(pairAmpFac), powerOfI(ny));
     if (qb_tile_try_pauli(q, ctrls, cs, nc, maskXY, maskYZ, mk(ampFac), pf)) return qb_tile_status();
-    int high = 63 - __builtin_clzll(maskXY), zero = 0;
-    OpPauliA op; op.ins = qb_make_ins(ctrls, cs, nc, &high, &zero, 1);
-    op.maskXY = (qindex)maskXY; op.maskYZ = (qindex)maskYZ; op.ampFac = mk(ampFac); op.pairFac = pf;
-    return qb_launch_tuple((cplx*)q->amps, q->numAmpsPerNode >> (1 + nc), op);
+    QB_FLUSH();
+    qb_cplx pfc = {pf.x, pf.y};
+    return qb_pauli_raw(q, ctrls, cs, nc, maskXY, maskYZ, ampFac, pfc);
 }
 
 int qb_statevector_anyCtrlPauliTensorOrGadget_subB(const qb_state* q, const int* ctrls, const int* cs, int nc,
@@ -523,9 +535,10 @@ int qb_statevector_anyCtrlPauliTensorOrGadget_subB(const qb_state* q, const int*
 
 int qb_statevector_anyCtrlAnyTargZOrPhaseGadget_sub(const qb_state* q, const int* ctrls, const int* cs, int nc,
         const int* targs, int nt, qb_cplx f0, qb_cplx f1) {
-    QB_READY(); QB_CHECK_STATE(q); QB_CHECK_SUFFIX(ctrls, nc, q); QB_CHECK_SUFFIX(targs, nt, q);
+    QB_READY_NOFLUSH(); QB_CHECK_STATE(q); QB_CHECK_SUFFIX(ctrls, nc, q); QB_CHECK_SUFFIX(targs, nt, q);
     unsigned long long targMask = qb_make_mask(targs, nt);
     if (qb_tile_try_phase(q, ctrls, cs, nc, targMask, mk(f0), mk(f1))) return qb_tile_status();
+    QB_FLUSH();
     OpPhaseGadget op; op.ins = qb_make_ins(ctrls, cs, nc, nullptr, nullptr, 0);
     op.targMask = (qindex)targMask; op.f0 = mk(f0); op.f1 = mk(f1);
     return qb_launch_map((cplx*)q->amps, q->numAmpsPerNode >> nc, op);

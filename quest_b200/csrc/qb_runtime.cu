@@ -160,6 +160,12 @@ int qb_device_uuid(char out16[16]) {
     return 0;
 }
 
+int qb_flush(void) {
+    if (g_qb.device < 0) return 0;
+    QB_FLUSH();
+    return 0;
+}
+
 int qb_sync(void) {
     QB_READY();
     // gpu_sync() is a full device sync in the reference (gpu_config.cpp:382-390); the library issues
@@ -247,7 +253,11 @@ size_t qb_cache_bytes(void) { return (size_t)g_qb.cacheLen * sizeof(cplx); }
 
 unsigned long long qb_launch_count(void) { return g_qb.launches; }
 
-int qb_set_tile_engine(int enabled) { g_qb.tileEngine = enabled != 0; return 0; }
+int qb_set_tile_engine(int enabled) {
+    if (g_qb.device >= 0) QB_FLUSH();
+    g_qb.tileEngine = enabled != 0;
+    return 0;
+}
 
 int qb_statevec_getAmp_sub(const qb_state* q, qb_index ind, qb_cplx* out) {
     QB_REQUIRE(q && q->amps && out && ind >= 0 && ind < q->numAmpsPerNode, "getAmp: bad arguments");

@@ -12,3 +12,6 @@ int qb_tile_try_diag(const qb_state* q, const int* ctrls, const int* cs, int nc,
 int qb_tile_try_pauli(const qb_state* q, const int* ctrls, const int* cs, int nc, unsigned long long maskXY, unsigned long long maskYZ, cplx ampFac, cplx pairFac);
 int qb_tile_try_phase(const qb_state* q, const int* ctrls, const int* cs, int nc, unsigned long long targMask, cplx f0, cplx f1);
 int qb_tile_try_swap(const qb_state* q, const int* ctrls, const int* cs, int nc, int t1, int t2);
+
+// direct Pauli kernel from raw masks (pairFac already multiplied by i^numY); qb_gates.cu
+int qb_pauli_raw(const qb_state* q, const int* ctrls, const int* cs, int nc, unsigned long long maskXY, unsigned long long maskYZ, qb_cplx ampFac, qb_cplx pairFac);

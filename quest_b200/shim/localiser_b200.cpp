@@ -416,10 +416,17 @@ static void swapPrefixWithSuffix(Qureg qureg, vector<int> ctrls, vector<int> ctr
     int pairRank = rankWithFlipped(qureg, {prefixTarg});
     int suffixState = ! rankBit(qureg, prefixTarg);
 
-    // NVLink fast path: swap the two half-shards in place through peer memory, no packing and no buffer
-    if (ctrls.empty() && qureg.isGpuAccelerated && qb_p2p_is_available()) {
+    // NVLink fast path: swap the two half-shards in place through peer memory, no packing and no buffer.
+    // The link is only efficient on long contiguous runs, and the run length of "all amps with suffix bit s = b"
+    // is 2^s amps; a low suffix qubit is therefore first swapped LOCALLY (an HBM-speed pass) with the top suffix
+    // qubit, whose half-shard is one contiguous block:  SWAP(p,s) = SWAP(s,h) SWAP(p,h) SWAP(s,h).
+    if (ctrls.empty() && qureg.isGpuAccelerated && qureg.logNumAmpsPerNode >= 1 && qb_p2p_is_available()) {
         auto s = toState(qureg);
-        QB_CHECK( qb_p2p_swapHalves(&s, suffixTarg, pairRank) );
+        int top = (int) qureg.logNumAmpsPerNode - 1;
+        bool relocate = suffixTarg < 6 && suffixTarg != top;
+        if (relocate) accel_statevec_anyCtrlSwap_subA(qureg, {}, {}, suffixTarg, top);
+        QB_CHECK( qb_p2p_swapHalves(&s, relocate ? top : suffixTarg, pairRank) );
+        if (relocate) accel_statevec_anyCtrlSwap_subA(qureg, {}, {}, suffixTarg, top);
         return;
     }
 
@@ -496,23 +503,25 @@ static void denseOnSuffix(Qureg qureg, vector<int> ctrls, vector<int> ctrlStates
     accel_statevec_anyCtrlAnyTargDenseMatr_sub(qureg, ctrls, ctrlStates, targs, matr, conj);
 }
 
-// finds, for every prefix target, the lowest suffix qubit that is not a target; a control sitting there trades
-// places with the target  [localiser.cpp:146-199 getCtrlsAndTargsSwappedToMinSuffix]
+// finds, for every prefix target, a suffix qubit that is not a target to trade places with; a control sitting
+// there moves to the vacated prefix position.  The reference takes the LOWEST free suffix qubit to help CPU
+// caches (localiser.cpp:146-199 getCtrlsAndTargsSwappedToMinSuffix); here the HIGHEST free one is taken: the
+// half-shard that has to cross NVLink is then one contiguous block, and the GPU gate kernels do not care.
 static tuple<vector<int>,vector<int>> relocateTargetsToSuffix(Qureg qureg, vector<int> ctrls, vector<int> targs) {
     qindex targMask = getBitMask(targs.data(), targs.size());
     qindex ctrlMask = getBitMask(ctrls.data(), ctrls.size());
-    int minFree = getIndOfNextRightmostZeroBit(targMask, -1);
+    int free = getIndOfNextLeftmostZeroBit(targMask, qureg.logNumAmpsPerNode);
     for (size_t i = 0; i < targs.size(); i++) {
         int targ = targs[i];
         if (isSuffix(qureg, targ))
             continue;
-        if (getBit(ctrlMask, minFree)) {
-            for (int& c : ctrls) if (c == minFree) { c = targ; break; }
-            ctrlMask = flipTwoBits(ctrlMask, minFree, targ);
+        if (getBit(ctrlMask, free)) {
+            for (int& c : ctrls) if (c == free) { c = targ; break; }
+            ctrlMask = flipTwoBits(ctrlMask, free, targ);
         }
-        targs[i] = minFree;
-        targMask = flipTwoBits(targMask, targ, minFree);
-        minFree = getIndOfNextRightmostZeroBit(targMask, minFree);
+        targs[i] = free;
+        targMask = flipTwoBits(targMask, targ, free);
+        free = getIndOfNextLeftmostZeroBit(targMask, free);
     }
     return {ctrls, targs};
 }

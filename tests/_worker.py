@@ -40,6 +40,10 @@ def main():
         if which != "ref":
             for name, inf in out["info"].items():
                 assert inf["isGpuAccelerated"] == 1, f"qureg {name} is not GPU-accelerated: refusing CPU path"
+        if which == "b200dist":
+            import ctypes
+            core = ctypes.CDLL(os.path.join(os.path.dirname(qa.B200_LIB), "libquest_b200.so"), mode=ctypes.RTLD_GLOBAL)
+            out["p2p_available"] = int(core.qb_p2p_is_available())
         outs.append(out)
     Q.finalizeQuESTEnv()
     pickle.dump(outs, open(dst, "wb"))

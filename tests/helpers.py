@@ -75,7 +75,7 @@ def num_gpus():
         return 0
 
 
-def run_programs_distributed(progs, world, timeout=1800, env=None, port=29731):
+def run_programs_distributed(progs, world, timeout=420, env=None, port=29731):
     """run the programs on `world` GPUs, one worker process per GPU (the launcher model of the backend:
     RANK / WORLD_SIZE / LOCAL_RANK / MASTER_PORT in the environment, like torchrun).  Returns rank 0's outputs
     with every density-matrix / distributed dump re-assembled from the per-rank shards (rank r holds the

@@ -26,6 +26,7 @@ def _check(progs, world, env=None):
     got = H.run_programs_distributed(progs, world, env=env)
     for k, (prog, g, w) in enumerate(zip(progs, got, want)):
         H.assert_outputs_match(g, w, label=f"P={world} prog[{k}]", int_exact_ops=_measure_ops(prog))
+    return got
 
 
 @pytest.mark.skipif(not WORLDS, reason="needs >= 2 GPUs")
@@ -33,8 +34,10 @@ def _check(progs, world, env=None):
 @pytest.mark.parametrize("p2p", ["1", "0"], ids=["nvlink-p2p", "nccl-only"])
 def test_statevector_gates_sharded(world, p2p):
     logp = world.bit_length() - 1
-    _check([P.gates_program(logp + 4, 6001, max_ctrls=2), P.gates_program(logp + 7, 6002, num_rounds=1),
-            P.cfg1_program(logp + 8, 6003, 120), P.cfg2_program(logp + 6, 6004, 60)], world, env={"QUEST_B200_P2P": p2p})
+    got = _check([P.gates_program(logp + 4, 6001, max_ctrls=2), P.gates_program(logp + 7, 6002, num_rounds=1),
+                  P.cfg1_program(logp + 8, 6003, 120), P.cfg2_program(logp + 6, 6004, 60)], world, env={"QUEST_B200_P2P": p2p})
+    # the fused NVLink peer-memory kernels must really have been the path under test (and really off otherwise)
+    assert got[0]["p2p_available"] == int(p2p), "NVLink peer-memory path availability is not what the test asked for"
 
 
 @pytest.mark.skipif(not WORLDS, reason="needs >= 2 GPUs")

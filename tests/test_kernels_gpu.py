@@ -509,3 +509,99 @@ def test_errors_are_loud():
     with pytest.raises(capi.QbError):
         capi.call("qb_statevec_anyCtrlOneTargDenseMatr_subA", dev.ref, capi.ints([]), capi.ints([]), 0, 9, capi.cplx_array(np.eye(2)))
     assert capi.lib().qb_launch_count() > 0
+
+
+def _random_fusable_op(rng, n, st, dev, prefix_bits=0):
+    """apply one random fusable gate to both the oracle state and the device state (queued by the tile engine)"""
+    kind = rng.choice(["dense1", "dense2", "pauli", "swap", "diag1", "diag2", "parity", "ladder"])
+    nc = int(rng.integers(0, 3))
+    if kind == "dense1":
+        c, s, t = ctrl_targ(rng, n, nc, 1); m = rand_unitary(rng, 2)
+        capi.call("qb_statevec_anyCtrlOneTargDenseMatr_subA", dev.ref, capi.ints(c), capi.ints(s), nc, t[0], capi.cplx_array(m))
+        qo.statevec_anyCtrlOneTargDenseMatr_subA(st, c, s, t[0], m)
+    elif kind == "dense2":
+        c, s, t = ctrl_targ(rng, n, nc, 2); m = rand_unitary(rng, 4)
+        capi.call("qb_statevec_anyCtrlTwoTargDenseMatr_sub", dev.ref, capi.ints(c), capi.ints(s), nc, t[0], t[1], capi.cplx_array(m))
+        qo.statevec_anyCtrlTwoTargDenseMatr_sub(st, c, s, t[0], t[1], m)
+    elif kind == "pauli":
+        k = int(rng.integers(1, 5)); c, s, t = ctrl_targ(rng, n, nc, k)
+        chars = rng.choice(list("XYZ"), size=k)
+        if not any(ch in "XY" for ch in chars):
+            chars[0] = "Y"
+        x = [q for ch, q in zip(chars, t) if ch == "X"]; y = [q for ch, q in zip(chars, t) if ch == "Y"]; z = [q for ch, q in zip(chars, t) if ch == "Z"]
+        th = rng.uniform(0, 6); af, pf = complex(np.cos(th)), 1j * np.sin(th)
+        capi.call("qb_statevector_anyCtrlPauliTensorOrGadget_subA", dev.ref, capi.ints(c), capi.ints(s), nc,
+                  capi.ints(x), len(x), capi.ints(y), len(y), capi.ints(z), len(z), capi.cplx(af), capi.cplx(pf))
+        qo.statevector_anyCtrlPauliTensorOrGadget_subA(st, c, s, x, y, z, af, pf)
+    elif kind == "swap":
+        c, s, t = ctrl_targ(rng, n, nc, 2)
+        capi.call("qb_statevec_anyCtrlSwap_subA", dev.ref, capi.ints(c), capi.ints(s), nc, t[0], t[1])
+        qo.statevec_anyCtrlSwap_subA(st, c, s, t[0], t[1])
+    elif kind == "diag1":
+        c, s, _ = ctrl_targ(rng, n, nc, 0)
+        t = int(rng.choice([q for q in range(n + prefix_bits) if q not in c])); e = np.exp(1j * rng.uniform(0, 6, 2))
+        capi.call("qb_statevec_anyCtrlOneTargDiagMatr_sub", dev.ref, capi.ints(c), capi.ints(s), nc, t, capi.cplx_array(e))
+        qo.statevec_anyCtrlOneTargDiagMatr_sub(st, c, s, t, e)
+    elif kind == "diag2":
+        c, s, _ = ctrl_targ(rng, n, nc, 0)
+        t = [int(q) for q in rng.choice([q for q in range(n + prefix_bits) if q not in c], size=2, replace=False)]
+        e = np.exp(1j * rng.uniform(0, 6, 4))
+        capi.call("qb_statevec_anyCtrlTwoTargDiagMatr_sub", dev.ref, capi.ints(c), capi.ints(s), nc, t[0], t[1], capi.cplx_array(e))
+        qo.statevec_anyCtrlTwoTargDiagMatr_sub(st, c, s, t[0], t[1], e)
+    elif kind == "parity":
+        k = int(rng.integers(1, 6)); c, s, t = ctrl_targ(rng, n, nc, k); f0, f1 = np.exp(1j * rng.uniform(0, 6, 2))
+        capi.call("qb_statevector_anyCtrlAnyTargZOrPhaseGadget_sub", dev.ref, capi.ints(c), capi.ints(s), nc, capi.ints(t), k, capi.cplx(f0), capi.cplx(f1))
+        qo.statevector_anyCtrlAnyTargZOrPhaseGadget_sub(st, c, s, t, f0, f1)
+    else:
+        # a QFT-style ladder: controlled phases sharing one qubit (merged into a phase star by the engine)
+        centre = int(rng.integers(n)); others = [q for q in range(n) if q != centre]
+        for o in rng.choice(others, size=min(len(others), int(rng.integers(2, 9))), replace=False):
+            o = int(o); th = float(rng.uniform(0, 6)); e = [1, np.exp(1j * th)]
+            targ, ctrl = (centre, o) if rng.integers(2) else (o, centre)
+            capi.call("qb_statevec_anyCtrlOneTargDiagMatr_sub", dev.ref, capi.ints([ctrl]), capi.ints([1]), 1, targ, capi.cplx_array(e))
+            qo.statevec_anyCtrlOneTargDiagMatr_sub(st, [ctrl], [1], targ, e)
+
+
+@pytest.mark.parametrize("n", [13, 14, 17, 20, 22])
+@pytest.mark.parametrize("rank,logNodes", [(0, 0), (2, 2)])
+def test_fused_gate_sequences(n, rank, logNodes):
+    """the tile engine proper: long random runs of fusable gates are queued, planned into multi-gate passes and
+    executed by the TMA tile kernel; the result must equal gate-by-gate application by the oracle"""
+    capi.call("qb_set_tile_engine", 1)
+    rng = np.random.default_rng(1300 + n + rank)
+    for trial in range(3):
+        st = rand_sv(rng, n + logNodes, rank, logNodes); dev = Dev(st)
+        launches0 = capi.lib().qb_launch_count()
+        nops = [5, 40, 120][trial]
+        for _ in range(nops):
+            _random_fusable_op(rng, n, st, dev, prefix_bits=logNodes)
+        err = rel_l2(dev.host(), st.amps)
+        launches = capi.lib().qb_launch_count() - launches0
+        assert err <= TOL * 5, f"fused n={n} ops={nops}: rel-L2 {err:.3e}"
+        assert launches < nops, f"no fusion happened: {launches} launches for {nops} gates"
+
+
+@pytest.mark.parametrize("n", [13, 18, 21])
+def test_fused_qft_matches_gate_by_gate(n):
+    """the QFT ladder (api/operations.cpp:1934-1953) through the phase-star merge vs the same gates one at a time"""
+    rng = np.random.default_rng(1400 + n)
+    psi = rand_sv(rng, n)
+    results = []
+    for engine in (1, 0):
+        capi.call("qb_set_tile_engine", engine)
+        st = qo.State(psi.amps.copy(), n); dev = Dev(st)
+        h = np.array([[1, 1], [1, -1]]) / np.sqrt(2)
+        for t in range(n - 1, -1, -1):
+            capi.call("qb_statevec_anyCtrlOneTargDenseMatr_subA", dev.ref, capi.ints([]), capi.ints([]), 0, t, capi.cplx_array(h))
+            for m in range(t):
+                e = [1, np.exp(1j * np.pi / (1 << (m + 1)))]
+                capi.call("qb_statevec_anyCtrlOneTargDiagMatr_sub", dev.ref, capi.ints([t - m - 1]), capi.ints([1]), 1, t, capi.cplx_array(e))
+        for t in range(n // 2):
+            capi.call("qb_statevec_anyCtrlSwap_subA", dev.ref, capi.ints([]), capi.ints([]), 0, t, n - 1 - t)
+        results.append(dev.host())
+    capi.call("qb_set_tile_engine", 1)
+    # reference: DFT with the convention of tests/utils/linalg.cpp:160-176
+    want = np.fft.ifft(psi.amps) * np.sqrt(1 << n)
+    assert rel_l2(results[1], want) <= 1e-11, "gate-by-gate QFT disagrees with the DFT"
+    assert rel_l2(results[0], want) <= 1e-11, "fused QFT disagrees with the DFT"
+    assert rel_l2(results[0], results[1]) <= TOL * 5
