@@ -12,13 +12,16 @@
 // amplitudes then split into 2^(n-12) independent TILES of 4096 amplitudes (64 KiB): fix the bits outside S.
 // Runs of controlled phase shifts sharing one qubit (the QFT's ladders, api/operations.cpp:1934-1953, which the
 // reference marks as a todo to merge) are folded into ONE "phase star" op evaluated from small lookup tables.
+// Inside a pass, gates are further grouped into ROUNDS: a round owns 4 of the 12 tile bits; every thread pulls the
+// 16 amplitudes spanned by those bits into registers, applies every gate of the round whose non-diagonal targets are
+// among the 4 bits (diagonal gates always qualify) and writes the 16 amplitudes back: one shared-memory round trip
+// and one barrier per ROUND instead of per gate.
 //
-// KERNEL.  One persistent CTA per SM (grid = #SMs), 512 threads, 3 stages x 64 KiB of shared memory.  Thread 0
-// drives the copy engine: cp.async.bulk (TMA, 1-D) loads the chunks of tile k+2 into a free stage, signalling an
-// mbarrier with complete_tx; all threads wait on the stage's mbarrier, apply the pass's gates to the tile in shared
-// memory (__syncthreads between gates), fence.proxy.async, and thread 0 writes the stage back with
-// cp.async.bulk.global.shared::cta (bulk async-group).  Loads of two tiles and the store of one are in flight while a
-// tile is being computed, so HBM stays busy; per tile the gates cost shared-memory bandwidth only.
+// KERNEL.  One persistent CTA per SM (grid = #SMs), 256 threads x 16 amplitudes, 3 stages x 64 KiB of shared memory.
+// Warp 0 also drives the copy engine: cp.async.bulk (TMA, 1-D) loads the chunks of tile k+2 into a free stage,
+// signalling an mbarrier with complete_tx; all threads wait on the stage's mbarrier, run the pass's rounds on the
+// tile, fence.proxy.async, and warp 0 writes the stage back with cp.async.bulk.global.shared::cta (bulk async-groups).
+// Loads of two tiles and the store of one are in flight while a tile is being computed.
 // Algorithmic bytes per pass: every gate of the pass counts its own 2*16*N/2^c bytes, physical bytes
 // are 2*16*N once per pass (or less: controls shared by every gate of a pass prune whole tiles before they are loaded).
 #include "qb_common.cuh"
@@ -33,13 +36,17 @@
 #define TILE_LOW 6
 #define TILE_AMPS (1 << TILE_BITS)
 #define TILE_STAGES 3
-#define TILE_THREADS 512
+#define TILE_THREADS 256
+#define RB 4                          // tile bits held in registers per round
+#define RAMPS (1 << RB)               // amplitudes per thread: TILE_THREADS * RAMPS == TILE_AMPS
 #define TILE_MAX_CHUNKS (1 << (TILE_BITS - TILE_LOW))
+#define MAX_OPS_PER_PASS 48
 #define QUEUE_MAX 512
 #define FUSE_MIN_LOG_AMPS 13          // smaller states use the direct kernels immediately
 #define STAR_SEGS 6                   // external-control tables: 6 segments x 6 bits of the global index
 
 enum { OP_DENSE1 = 0, OP_DENSE2, OP_PAULI, OP_SWAP, OP_DIAG, OP_PARITY, OP_STAR };
+enum { ROUND_REG = 0, ROUND_SMEM = 1 };
 
 // ------------------------------------------------------------------------------------------
 // queued gate, in global (local-shard) qubit coordinates
@@ -47,7 +54,7 @@ enum { OP_DENSE1 = 0, OP_DENSE2, OP_PAULI, OP_SWAP, OP_DIAG, OP_PARITY, OP_STAR 
 struct QOp {
     int kind;
     unsigned long long ctrlMask, ctrlVals;     // suffix controls
-    int t0, t1, numT;                          // targets; diag targets may be >= logN (prefix): resolved at enqueue
+    int t0, t1, numT;                          // targets (prefix diagonal targets are resolved at enqueue)
     unsigned long long maskA, maskB;           // pauli: XY, YZ; parity gadget: target mask
     cplx m[16];                                // matrix / diagonal / factors
     std::vector<std::pair<int,double>> star;   // OP_STAR: (other qubit, theta); centre qubit = t0
@@ -62,21 +69,23 @@ static bool s_inFlush = false;
 
 // device-side op, in tile coordinates
 struct TileOp {
-    int kind, p0, p1, numT;                    // in-tile positions (p < 0: target outside the tile, diag only)
-    int e0, e1;                                // global bit index of an external diag target
+    int kind, p0, p1, numT;                    // in-tile positions (p < 0: target outside the tile, diag/star only)
+    int e0, e1;                                // global bit index of an external diag target / star centre
+    int l0, l1;                                // register rounds: index (0..3) of the target bits among the round's bits
+    unsigned int lmaskA, lmaskB;               // register rounds: pauli XY mask / YZ-or-parity mask over the round's bits
     unsigned int inCtrlMask, inCtrlVals;
+    unsigned int inMaskA, inMaskB;             // pauli XY / YZ (or parity) masks over the 12 tile bits
     unsigned long long extCtrlMask, extCtrlVals;
-    unsigned int inMaskA, inMaskB;
     unsigned long long extMaskB;               // pauli / parity: sign bits outside the tile
-    int tab;                                   // OP_STAR: index of its table block
-    int pad;
+    int tab, pad;                              // OP_STAR: index of its table block
     cplx m[16];
 };
 
+struct RoundHdr { int kind, opBase, numOps, pad; int b[RB]; };
 struct StarTab { cplx in[2][64]; cplx ext[STAR_SEGS][64]; };
 
 struct PassHdr {
-    int numOps, numChunks, chunkAmps, pad;
+    int numOps, numRounds, numChunks, chunkAmps;
     qindex numTiles;
     BitIns tileIns;                            // tile number -> global base index (S bits zero, pruning controls set)
     qindex chunkOff[TILE_MAX_CHUNKS];          // global offset of chunk c inside a tile
@@ -110,128 +119,217 @@ template <int N> __device__ __forceinline__ void tma_wait_all() { asm volatile("
 __device__ __forceinline__ void fence_async_smem() { asm volatile("fence.proxy.async.shared::cta;" ::: "memory"); }
 
 __device__ __forceinline__ unsigned ins0(unsigned v, int p) { return ((v >> p) << (p + 1)) | (v & ((1u << p) - 1u)); }
+__device__ __forceinline__ cplx csel(bool c, cplx a, cplx b) { return mk(c ? a.x : b.x, c ? a.y : b.y); }
 
 // ------------------------------------------------------------------------------------------
-// applying one op to one tile held in shared memory
+// register-round gate bodies: v[u] is the amplitude whose round-bit pattern is u (bit k of u <-> round bit k);
+// `ok` has bit u set when amplitude u satisfies the gate's in-tile controls
 // ------------------------------------------------------------------------------------------
-__device__ __forceinline__ void apply_op(cplx* __restrict__ t, const TileOp& op, qindex base, const StarTab* __restrict__ tabs, cplx* scratch) {
+template <int K>
+__device__ __forceinline__ void reg_dense1(cplx (&v)[RAMPS], const cplx* __restrict__ m, unsigned ok) {
+    const cplx m00 = m[0], m01 = m[1], m10 = m[2], m11 = m[3];
+#pragma unroll
+    for (int u = 0; u < RAMPS; u++) {
+        if (u & (1 << K)) continue;
+        const int u1 = u | (1 << K);
+        cplx a0 = v[u], a1 = v[u1];
+        cplx n0 = cfma(m01, a1, cmul(m00, a0)), n1 = cfma(m11, a1, cmul(m10, a0));
+        const bool c = (ok >> u) & 1;
+        v[u] = csel(c, n0, a0); v[u1] = csel(c, n1, a1);
+    }
+}
+
+template <int K0, int K1>      // K0 < K1; matrix index bit 0 <-> K0, bit 1 <-> K1 (the host re-orders the matrix to make it so)
+__device__ __forceinline__ void reg_dense2(cplx (&v)[RAMPS], const cplx* __restrict__ mp, unsigned ok) {
+    cplx m[16];
+#pragma unroll
+    for (int i = 0; i < 16; i++) m[i] = mp[i];
+#pragma unroll
+    for (int u = 0; u < RAMPS; u++) {
+        if (u & ((1 << K0) | (1 << K1))) continue;
+        const int i1 = u | (1 << K0), i2 = u | (1 << K1), i3 = i1 | (1 << K1);
+        cplx a0 = v[u], a1 = v[i1], a2 = v[i2], a3 = v[i3];
+        const bool c = (ok >> u) & 1;
+        cplx n0 = cfma(m[3], a3, cfma(m[2], a2, cfma(m[1], a1, cmul(m[0], a0))));
+        cplx n1 = cfma(m[7], a3, cfma(m[6], a2, cfma(m[5], a1, cmul(m[4], a0))));
+        cplx n2 = cfma(m[11], a3, cfma(m[10], a2, cfma(m[9], a1, cmul(m[8], a0))));
+        cplx n3 = cfma(m[15], a3, cfma(m[14], a2, cfma(m[13], a1, cmul(m[12], a0))));
+        v[u] = csel(c, n0, a0); v[i1] = csel(c, n1, a1); v[i2] = csel(c, n2, a2); v[i3] = csel(c, n3, a3);
+    }
+}
+
+template <int K0, int K1>
+__device__ __forceinline__ void reg_swap(cplx (&v)[RAMPS], unsigned ok) {
+#pragma unroll
+    for (int u = 0; u < RAMPS; u++) {
+        if (!(u & (1 << K0)) || (u & (1 << K1))) continue;       // u has K0 = 1, K1 = 0
+        const int w = u ^ ((1 << K0) | (1 << K1));
+        const bool c = (ok >> u) & 1;
+        cplx a = v[u], b = v[w];
+        v[u] = csel(c, b, a); v[w] = csel(c, a, b);
+    }
+}
+
+// pairs (u, u ^ LXY); sign of amplitude u = (-1)^(parity of its Y/Z bits) = basePar ^ popc(u & lyz)
+template <int LXY>
+__device__ __forceinline__ void reg_pauli(cplx (&v)[RAMPS], unsigned lyz, int basePar, cplx af, cplx pf, unsigned ok) {
+    constexpr int H = (LXY & 8) ? 3 : (LXY & 4) ? 2 : (LXY & 2) ? 1 : 0;
+#pragma unroll
+    for (int u = 0; u < RAMPS; u++) {
+        if (u & (1 << H)) continue;
+        const int w = u ^ LXY;
+        const double sA = 1.0 - 2.0 * ((__popc(u & lyz) + basePar) & 1);
+        const double sB = 1.0 - 2.0 * ((__popc(w & lyz) + basePar) & 1);
+        cplx a = v[u], b = v[w];
+        cplx nA = cfma(pf, cscale(sB, b), cmul(af, a)), nB = cfma(pf, cscale(sA, a), cmul(af, b));
+        const bool c = (ok >> u) & 1;
+        v[u] = csel(c, nA, a); v[w] = csel(c, nB, b);
+    }
+}
+
+// ------------------------------------------------------------------------------------------
+// one register round on one tile
+// ------------------------------------------------------------------------------------------
+__device__ __forceinline__ void reg_round(cplx* __restrict__ t, const RoundHdr& rd, const TileOp* __restrict__ ops, qindex base,
+                                          const StarTab* __restrict__ tabs, const cplx* __restrict__ starF) {
     const int tid = threadIdx.x;
+    const int b0 = rd.b[0], b1 = rd.b[1], b2 = rd.b[2], b3 = rd.b[3];          // ascending tile-bit positions
+    const unsigned jb = ins0(ins0(ins0(ins0((unsigned)tid, b0), b1), b2), b3);
+    const unsigned o0 = 1u << b0, o1 = 1u << b1, o2 = 1u << b2, o3 = 1u << b3;
+#define OFF(u) ((((u) & 1) ? o0 : 0u) | (((u) & 2) ? o1 : 0u) | (((u) & 4) ? o2 : 0u) | (((u) & 8) ? o3 : 0u))
+    cplx v[RAMPS];
+#pragma unroll
+    for (int u = 0; u < RAMPS; u++) v[u] = t[jb | OFF(u)];
+
+    for (int o = 0; o < rd.numOps; o++) {
+        const TileOp& op = ops[rd.opBase + o];
+        if (((unsigned long long)base & op.extCtrlMask) != op.extCtrlVals) continue;      // tile-uniform
+        unsigned ok = 0xFFFFu;
+        if (op.inCtrlMask) {
+            ok = 0;
+#pragma unroll
+            for (int u = 0; u < RAMPS; u++) ok |= (unsigned)(((jb | OFF(u)) & op.inCtrlMask) == op.inCtrlVals) << u;
+        }
+        switch (op.kind) {
+        case OP_DENSE1:
+            switch (op.l0) {
+            case 0: reg_dense1<0>(v, op.m, ok); break;
+            case 1: reg_dense1<1>(v, op.m, ok); break;
+            case 2: reg_dense1<2>(v, op.m, ok); break;
+            default: reg_dense1<3>(v, op.m, ok); break;
+            }
+            break;
+        case OP_DENSE2:
+            switch (op.l0 * 4 + op.l1) {
+            case 1: reg_dense2<0, 1>(v, op.m, ok); break;
+            case 2: reg_dense2<0, 2>(v, op.m, ok); break;
+            case 3: reg_dense2<0, 3>(v, op.m, ok); break;
+            case 6: reg_dense2<1, 2>(v, op.m, ok); break;
+            case 7: reg_dense2<1, 3>(v, op.m, ok); break;
+            default: reg_dense2<2, 3>(v, op.m, ok); break;
+            }
+            break;
+        case OP_SWAP:
+            switch (op.l0 * 4 + op.l1) {
+            case 1: reg_swap<0, 1>(v, ok); break;
+            case 2: reg_swap<0, 2>(v, ok); break;
+            case 3: reg_swap<0, 3>(v, ok); break;
+            case 6: reg_swap<1, 2>(v, ok); break;
+            case 7: reg_swap<1, 3>(v, ok); break;
+            default: reg_swap<2, 3>(v, ok); break;
+            }
+            break;
+        case OP_PAULI: {
+            // sign bits of the Y/Z mask: those among the round's bits vary with u, the rest is fixed for this thread
+            const int basePar = (__popc(jb & op.inMaskB) + parity64((unsigned long long)base & op.extMaskB)) & 1;
+            const cplx af = op.m[0], pf = op.m[1];
+            const unsigned lyz = op.lmaskB;
+            switch (op.lmaskA) {
+#define PC(X) case X: reg_pauli<X>(v, lyz, basePar, af, pf, ok); break;
+            PC(1) PC(2) PC(3) PC(4) PC(5) PC(6) PC(7) PC(8) PC(9) PC(10) PC(11) PC(12) PC(13) PC(14)
+            default: reg_pauli<15>(v, lyz, basePar, af, pf, ok); break;
+#undef PC
+            }
+        } break;
+        case OP_DIAG: {
+            const cplx m0 = op.m[0], m1 = op.m[1], m2 = op.m[2], m3 = op.m[3];
+            const int x0 = (op.p0 < 0) ? getBit(base, op.e0) : 0;
+            const int x1 = (op.numT > 1 && op.p1 < 0) ? getBit(base, op.e1) : 0;
+#pragma unroll
+            for (int u = 0; u < RAMPS; u++) {
+                const unsigned j = jb | OFF(u);
+                const int k0 = (op.p0 < 0) ? x0 : ((j >> op.p0) & 1);
+                const int k1 = (op.numT > 1) ? ((op.p1 < 0) ? x1 : ((j >> op.p1) & 1)) : 0;
+                const cplx f = k1 ? (k0 ? m3 : m2) : (k0 ? m1 : m0);
+                v[u] = csel((ok >> u) & 1, cmul(v[u], f), v[u]);
+            }
+        } break;
+        case OP_PARITY: {
+            const cplx f0 = op.m[0], f1 = op.m[1];
+            const int extPar = parity64((unsigned long long)base & op.extMaskB);
+#pragma unroll
+            for (int u = 0; u < RAMPS; u++) {
+                const unsigned j = jb | OFF(u);
+                const int par = (__popc(j & op.inMaskA) + extPar) & 1;
+                v[u] = csel((ok >> u) & 1, cmul(v[u], par ? f1 : f0), v[u]);
+            }
+        } break;
+        case OP_STAR: {
+            // amplitudes with centre bit 1 gain exp(i sum_c theta_c bit_c): product of per-segment table entries
+            const StarTab& tb = tabs[op.tab];
+            if (op.p0 < 0 && !getBit(base, op.e0)) break;
+            const cplx f = starF[rd.opBase + o];
+#pragma unroll
+            for (int u = 0; u < RAMPS; u++) {
+                const unsigned j = jb | OFF(u);
+                const bool on = (op.p0 < 0) ? true : ((j >> op.p0) & 1);
+                cplx e = cmul(cmul(__ldg(&tb.in[0][j & 63]), __ldg(&tb.in[1][j >> 6])), f);
+                v[u] = csel(on, cmul(v[u], e), v[u]);
+            }
+        } break;
+        }
+    }
+#pragma unroll
+    for (int u = 0; u < RAMPS; u++) t[jb | OFF(u)] = v[u];
+#undef OFF
+}
+
+// shared-memory fallback for the one gate shape that cannot live in a 4-bit register round:
+// Pauli strings with X/Y on more than four tile bits
+__device__ __forceinline__ void smem_pauli(cplx* __restrict__ t, const TileOp& op, qindex base) {
     const unsigned cm = op.inCtrlMask, cv = op.inCtrlVals;
-    switch (op.kind) {
-    case OP_DENSE1: {
-        const int p = op.p0; const unsigned bit = 1u << p;
-        const cplx m00 = op.m[0], m01 = op.m[1], m10 = op.m[2], m11 = op.m[3];
-        for (unsigned n = tid; n < TILE_AMPS / 2; n += TILE_THREADS) {
-            unsigned j0 = ins0(n, p);
-            if ((j0 & cm) != cv) continue;
-            cplx a0 = t[j0], a1 = t[j0 | bit];
-            t[j0] = cfma(m01, a1, cmul(m00, a0));
-            t[j0 | bit] = cfma(m11, a1, cmul(m10, a0));
-        }
-    } break;
-    case OP_DENSE2: {
-        const int lo = min(op.p0, op.p1), hi = max(op.p0, op.p1);
-        const unsigned b0 = 1u << op.p0, b1 = 1u << op.p1;
-        for (unsigned n = tid; n < TILE_AMPS / 4; n += TILE_THREADS) {
-            unsigned j = ins0(ins0(n, lo), hi);
-            if ((j & cm) != cv) continue;
-            cplx a0 = t[j], a1 = t[j | b0], a2 = t[j | b1], a3 = t[j | b0 | b1];
-#pragma unroll
-            for (int r = 0; r < 4; r++) {
-                cplx v = cfma(op.m[4 * r + 3], a3, cfma(op.m[4 * r + 2], a2, cfma(op.m[4 * r + 1], a1, cmul(op.m[4 * r], a0))));
-                t[j | ((r & 1) ? b0 : 0u) | ((r & 2) ? b1 : 0u)] = v;
-            }
-        }
-    } break;
-    case OP_PAULI: {
-        const unsigned xy = op.inMaskA, yz = op.inMaskB;
-        const int h = 31 - __clz(xy);
-        const int extPar = parity64((unsigned long long)base & op.extMaskB);
-        const cplx af = op.m[0], pf = op.m[1];
-        for (unsigned n = tid; n < TILE_AMPS / 2; n += TILE_THREADS) {
-            unsigned jA = ins0(n, h);
-            if ((jA & cm) != cv) continue;
-            unsigned jB = jA ^ xy;
-            double sA = 1.0 - 2.0 * ((__popc(jA & yz) + extPar) & 1);
-            double sB = 1.0 - 2.0 * ((__popc(jB & yz) + extPar) & 1);
-            cplx a = t[jA], b = t[jB];
-            t[jA] = cfma(pf, cscale(sB, b), cmul(af, a));
-            t[jB] = cfma(pf, cscale(sA, a), cmul(af, b));
-        }
-    } break;
-    case OP_SWAP: {
-        const int lo = min(op.p0, op.p1), hi = max(op.p0, op.p1);
-        const unsigned b0 = 1u << op.p0, b1 = 1u << op.p1;
-        for (unsigned n = tid; n < TILE_AMPS / 4; n += TILE_THREADS) {
-            unsigned j = ins0(ins0(n, lo), hi);
-            if ((j & cm) != cv) continue;
-            cplx a = t[j | b0], b = t[j | b1];
-            t[j | b0] = b; t[j | b1] = a;
-        }
-    } break;
-    case OP_DIAG: {
-        // element index bit k <- target k; external targets read their (tile-constant) bit from the base index
-        const int x0 = (op.p0 < 0) ? getBit(base, op.e0) : 0;
-        const int x1 = (op.numT > 1 && op.p1 < 0) ? getBit(base, op.e1) : 0;
-        for (unsigned j = tid; j < TILE_AMPS; j += TILE_THREADS) {
-            if ((j & cm) != cv) continue;
-            int k = (op.p0 < 0) ? x0 : ((j >> op.p0) & 1);
-            if (op.numT > 1) k |= ((op.p1 < 0) ? x1 : ((j >> op.p1) & 1)) << 1;
-            t[j] = cmul(t[j], op.m[k]);
-        }
-    } break;
-    case OP_PARITY: {
-        const int extPar = parity64((unsigned long long)base & op.extMaskB);
-        for (unsigned j = tid; j < TILE_AMPS; j += TILE_THREADS) {
-            if ((j & cm) != cv) continue;
-            int par = (__popc(j & op.inMaskA) + extPar) & 1;
-            t[j] = cmul(t[j], op.m[par]);
-        }
-    } break;
-    case OP_STAR: {
-        // all amplitudes with centre bit = 1 gain exp(i * sum_c theta_c * bit_c): product of per-segment table entries
-        const StarTab& tb = tabs[op.tab];
-        if (op.p0 < 0 && !getBit(base, op.e0)) break;
-        if (tid == 0) {
-            cplx f = mk(1, 0);
-#pragma unroll
-            for (int s = 0; s < STAR_SEGS; s++) f = cmul(f, tb.ext[s][(base >> (6 * s)) & 63]);
-            scratch[0] = f;
-        }
-        __syncthreads();
-        const cplx f = scratch[0];
-        if (op.p0 >= 0) {
-            const int p = op.p0;
-            for (unsigned n = tid; n < TILE_AMPS / 2; n += TILE_THREADS) {
-                unsigned j = ins0(n, p) | (1u << p);
-                cplx e = cmul(cmul(tb.in[0][j & 63], tb.in[1][j >> 6]), f);
-                t[j] = cmul(t[j], e);
-            }
-        } else {
-            for (unsigned j = tid; j < TILE_AMPS; j += TILE_THREADS) {
-                cplx e = cmul(cmul(tb.in[0][j & 63], tb.in[1][j >> 6]), f);
-                t[j] = cmul(t[j], e);
-            }
-        }
-        __syncthreads();       // scratch[0] is reused by the next star
-    } break;
+    const unsigned xy = op.inMaskA, yz = op.inMaskB;
+    const int h = 31 - __clz(xy);
+    const int extPar = parity64((unsigned long long)base & op.extMaskB);
+    const cplx af = op.m[0], pf = op.m[1];
+    for (unsigned n = threadIdx.x; n < TILE_AMPS / 2; n += TILE_THREADS) {
+        unsigned jA = ins0(n, h);
+        if ((jA & cm) != cv) continue;
+        unsigned jB = jA ^ xy;
+        double sA = 1.0 - 2.0 * ((__popc(jA & yz) + extPar) & 1);
+        double sB = 1.0 - 2.0 * ((__popc(jB & yz) + extPar) & 1);
+        cplx a = t[jA], b = t[jB];
+        t[jA] = cfma(pf, cscale(sB, b), cmul(af, a));
+        t[jB] = cfma(pf, cscale(sA, a), cmul(af, b));
     }
 }
 
 __global__ void __launch_bounds__(TILE_THREADS, 1) k_tile_pass(cplx* __restrict__ amps, const PassHdr* __restrict__ hdrp,
-                                                               const TileOp* __restrict__ gops, const StarTab* __restrict__ tabs) {
+        const RoundHdr* __restrict__ grounds, const TileOp* __restrict__ gops, const StarTab* __restrict__ tabs) {
     extern __shared__ __align__(128) unsigned char smem_raw[];
     cplx* stageBuf = reinterpret_cast<cplx*>(smem_raw);                                  // [STAGES][TILE_AMPS]
     TileOp* ops = reinterpret_cast<TileOp*>(smem_raw + (size_t)TILE_STAGES * TILE_AMPS * sizeof(cplx));
     __shared__ unsigned long long full[TILE_STAGES];
     __shared__ PassHdr hdr;
-    __shared__ cplx scratch[2];
+    __shared__ RoundHdr rounds[MAX_OPS_PER_PASS];
+    __shared__ cplx starF[MAX_OPS_PER_PASS];
 
     const int tid = threadIdx.x;
     for (int i = tid; i < (int)(sizeof(PassHdr) / 4); i += TILE_THREADS) ((int*)&hdr)[i] = ((const int*)hdrp)[i];
     __syncthreads();
-    const int numOps = hdr.numOps;
+    const int numOps = hdr.numOps, numRounds = hdr.numRounds;
     for (int i = tid; i < numOps * (int)(sizeof(TileOp) / 4); i += TILE_THREADS) ((int*)ops)[i] = ((const int*)gops)[i];
+    for (int i = tid; i < numRounds * (int)(sizeof(RoundHdr) / 4); i += TILE_THREADS) ((int*)rounds)[i] = ((const int*)grounds)[i];
     if (tid == 0) {
         for (int s = 0; s < TILE_STAGES; s++) mbar_init(&full[s], 1);
         asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
@@ -243,16 +341,20 @@ __global__ void __launch_bounds__(TILE_THREADS, 1) k_tile_pass(cplx* __restrict_
     const unsigned chunkBytes = (unsigned)hdr.chunkAmps * (unsigned)sizeof(cplx);
     const qindex myCount = (numTiles > (qindex)blockIdx.x) ? (numTiles - blockIdx.x + gridDim.x - 1) / gridDim.x : 0;
 
-    auto issue_load = [&](qindex k) {          // thread 0 only
+    // warp 0 drives the copy engine; its 32 lanes share the chunks of a tile so that no single thread serialises
+    // the (up to 64 + 64) bulk-copy issues of a tile while the others wait for it at the next barrier
+    const int lane = tid & 31;
+    auto issue_load = [&](qindex k) {          // all lanes of warp 0
         const int s = (int)(k % TILE_STAGES);
         const qindex base = hdr.tileIns((qindex)blockIdx.x + k * gridDim.x);
-        mbar_expect_tx(&full[s], TILE_AMPS * (unsigned)sizeof(cplx));
+        if (lane == 0) mbar_expect_tx(&full[s], TILE_AMPS * (unsigned)sizeof(cplx));
+        __syncwarp();
         cplx* dst = stageBuf + (size_t)s * TILE_AMPS;
-        for (int c = 0; c < numChunks; c++)
+        for (int c = lane; c < numChunks; c += 32)
             tma_load(dst + (size_t)c * hdr.chunkAmps, amps + base + hdr.chunkOff[c], chunkBytes, &full[s]);
     };
 
-    if (tid == 0) {
+    if (tid < 32) {
         if (myCount > 0) issue_load(0);
         if (myCount > 1) issue_load(1);
     }
@@ -262,26 +364,42 @@ __global__ void __launch_bounds__(TILE_THREADS, 1) k_tile_pass(cplx* __restrict_
         const unsigned parity = (unsigned)((k / TILE_STAGES) & 1);
         const qindex base = hdr.tileIns((qindex)blockIdx.x + k * gridDim.x);
         cplx* t = stageBuf + (size_t)s * TILE_AMPS;
-        mbar_wait(&full[s], parity);
 
-        for (int o = 0; o < numOps; o++) {
-            const TileOp& op = ops[o];
-            if (((unsigned long long)base & op.extCtrlMask) == op.extCtrlVals)     // tile-uniform: no divergence
-                apply_op(t, op, base, tabs, scratch);
+        // per-tile factor of every phase star: the part of its phase that depends on bits OUTSIDE the tile
+        if (tid < numOps && ops[tid].kind == OP_STAR) {
+            const StarTab& tb = tabs[ops[tid].tab];
+            cplx f = mk(1, 0);
+#pragma unroll
+            for (int sg = 0; sg < STAR_SEGS; sg++) f = cmul(f, __ldg(&tb.ext[sg][(base >> (6 * sg)) & 63]));
+            starF[tid] = f;
+        }
+        mbar_wait(&full[s], parity);
+        __syncthreads();
+
+        for (int r = 0; r < numRounds; r++) {
+            const RoundHdr& rd = rounds[r];
+            if (rd.kind == ROUND_REG) {
+                reg_round(t, rd, ops, base, tabs, starF);
+            } else {
+                const TileOp& op = ops[rd.opBase];
+                if (((unsigned long long)base & op.extCtrlMask) == op.extCtrlVals) smem_pauli(t, op, base);
+            }
             __syncthreads();
         }
         fence_async_smem();
         __syncthreads();
-        if (tid == 0) {
-            for (int c = 0; c < numChunks; c++)
+        if (tid < 32) {
+            for (int c = lane; c < numChunks; c += 32)
                 tma_store(amps + base + hdr.chunkOff[c], t + (size_t)c * hdr.chunkAmps, chunkBytes);
             tma_commit();
-            // the stage that tile k+2 will use held tile k-1, whose store was committed one iteration ago
+            // the stage that tile k+2 will use held tile k-1, whose stores (one bulk group per lane) were
+            // committed one iteration ago: every lane waits for its own, then the warp re-converges
             tma_wait_read<1>();
+            __syncwarp();
             if (k + 2 < myCount) issue_load(k + 2);
         }
     }
-    if (tid == 0) tma_wait_all<0>();
+    if (tid < 32) tma_wait_all<0>();
 }
 
 // ------------------------------------------------------------------------------------------
@@ -298,13 +416,14 @@ static inline unsigned long long nonDiagTargets(const QOp& o) {
     }
 }
 
-// run the direct (unfused) kernel for one queued op
 static int run_direct(const qb_state* q, const QOp& o);
 
-static int s_maxOpsPerPass = 48;
+struct Emitted {
+    std::vector<PassHdr> hdrs; std::vector<RoundHdr> rounds; std::vector<TileOp> ops; std::vector<StarTab> tabs;
+    std::vector<int> opBase, roundBase;
+};
 
-static int emit_pass(const qb_state* q, const std::vector<QOp>& ops, const Pass& pass,
-                     std::vector<PassHdr>& hdrs, std::vector<TileOp>& tops, std::vector<StarTab>& tabs, std::vector<int>& opCount) {
+static void emit_pass(const qb_state* q, const std::vector<QOp>& ops, const Pass& pass, Emitted& E) {
     const int n = q->logNumAmpsPerNode;
     // tile bit set S: the low bits, the required high bits, then filler (lowest unused bits) up to TILE_BITS
     unsigned long long S = ((1ULL << TILE_LOW) - 1) | pass.high;
@@ -313,14 +432,13 @@ static int emit_pass(const qb_state* q, const std::vector<QOp>& ops, const Pass&
     for (int b = 0; b < 64; b++) pos[b] = -1;
     for (int b = 0; b < n; b++) if ((S >> b) & 1) { pos[b] = T; sbits[T++] = b; }
     // controls shared (same qubit, same value) by EVERY op of the pass and lying outside S prune whole tiles
-    unsigned long long common = ~0ULL, commonVals = 0;
+    unsigned long long common = 0, commonVals = 0;
     for (size_t i = 0; i < pass.opIdx.size(); i++) {
         const QOp& o = ops[pass.opIdx[i]];
         unsigned long long m = o.ctrlMask & ~S;
         if (i == 0) { common = m; commonVals = o.ctrlVals & m; }
         else { common &= m; common &= ~((o.ctrlVals ^ commonVals) & common); commonVals &= common; }
     }
-    if (pass.opIdx.empty()) common = 0;
 
     PassHdr h; memset(&h, 0, sizeof h);
     int contiguous = 0; while (contiguous < T && sbits[contiguous] == contiguous) contiguous++;
@@ -331,7 +449,6 @@ static int emit_pass(const qb_state* q, const std::vector<QOp>& ops, const Pass&
         for (int b = contiguous; b < T; b++) if ((c >> (b - contiguous)) & 1) off |= (qindex)1 << sbits[b];
         h.chunkOff[c] = off;
     }
-    // tile enumeration inserts zeros at S bits and the pruning-control bits (with their required values)
     int fixedQ[64], fixedV[64], nf = 0;
     for (int b = 0; b < n; b++) {
         if ((S >> b) & 1) { fixedQ[nf] = b; fixedV[nf++] = 0; }
@@ -341,24 +458,25 @@ static int emit_pass(const qb_state* q, const std::vector<QOp>& ops, const Pass&
     h.numTiles = (qindex)1 << (n - nf);
     h.numOps = (int)pass.opIdx.size();
 
-    const unsigned long long inMaskAll = S;
     auto toIn = [&](unsigned long long gm) { unsigned v = 0; for (int p = 0; p < T; p++) if ((gm >> sbits[p]) & 1) v |= 1u << p; return v; };
+    const size_t opStart = E.ops.size();
+    std::vector<unsigned> needIn;            // per op: tile-bit positions its non-diagonal targets occupy
     for (int idx : pass.opIdx) {
         const QOp& o = ops[idx];
         TileOp t; memset(&t, 0, sizeof t);
         t.kind = o.kind; t.numT = o.numT;
-        t.inCtrlMask = toIn(o.ctrlMask & inMaskAll); t.inCtrlVals = toIn(o.ctrlVals & o.ctrlMask & inMaskAll);
-        t.extCtrlMask = o.ctrlMask & ~inMaskAll; t.extCtrlVals = o.ctrlVals & t.extCtrlMask;
-        t.p0 = t.p1 = -1; t.e0 = t.e1 = 0;
+        t.inCtrlMask = toIn(o.ctrlMask & S); t.inCtrlVals = toIn(o.ctrlVals & o.ctrlMask & S);
+        t.extCtrlMask = o.ctrlMask & ~S; t.extCtrlVals = o.ctrlVals & t.extCtrlMask;
+        t.p0 = t.p1 = -1;
         for (int i = 0; i < 16; i++) t.m[i] = o.m[i];
         switch (o.kind) {
         case OP_DENSE1: t.p0 = pos[o.t0]; break;
         case OP_DENSE2: case OP_SWAP: t.p0 = pos[o.t0]; t.p1 = pos[o.t1]; break;
-        case OP_PAULI: t.inMaskA = toIn(o.maskA); t.inMaskB = toIn(o.maskB & inMaskAll); t.extMaskB = o.maskB & ~inMaskAll; break;
-        case OP_PARITY: t.inMaskA = toIn(o.maskA & inMaskAll); t.extMaskB = o.maskA & ~inMaskAll; break;
+        case OP_PAULI: t.inMaskA = toIn(o.maskA); t.inMaskB = toIn(o.maskB & S); t.extMaskB = o.maskB & ~S; break;
+        case OP_PARITY: t.inMaskA = toIn(o.maskA & S); t.extMaskB = o.maskA & ~S; break;
         case OP_DIAG:
-            t.p0 = (o.t0 < n) ? pos[o.t0] : -1; t.e0 = o.t0;
-            if (o.numT > 1) { t.p1 = (o.t1 < n) ? pos[o.t1] : -1; t.e1 = o.t1; }
+            t.p0 = pos[o.t0]; t.e0 = o.t0;
+            if (o.numT > 1) { t.p1 = pos[o.t1]; t.e1 = o.t1; }
             break;
         case OP_STAR: {
             t.p0 = pos[o.t0]; t.e0 = o.t0;
@@ -371,15 +489,77 @@ static int emit_pass(const qb_state* q, const std::vector<QOp>& ops, const Pass&
             }
             for (int s = 0; s < 2; s++) for (int v = 0; v < 64; v++) tb.in[s][v] = mk((double)cosl(angIn[s][v]), (double)sinl(angIn[s][v]));
             for (int s = 0; s < STAR_SEGS; s++) for (int v = 0; v < 64; v++) tb.ext[s][v] = mk((double)cosl(angExt[s][v]), (double)sinl(angExt[s][v]));
-            t.tab = (int)tabs.size();
-            tabs.push_back(tb);
+            t.tab = (int)E.tabs.size();
+            E.tabs.push_back(tb);
         } break;
         }
-        tops.push_back(t);
+        unsigned need = 0;
+        if (o.kind == OP_DENSE1) need = 1u << t.p0;
+        else if (o.kind == OP_DENSE2 || o.kind == OP_SWAP) need = (1u << t.p0) | (1u << t.p1);
+        else if (o.kind == OP_PAULI) need = t.inMaskA;
+        needIn.push_back(need);
+        E.ops.push_back(t);
     }
-    hdrs.push_back(h);
-    opCount.push_back(h.numOps);
-    return 0;
+
+    // rounds: greedily pack consecutive ops whose non-diagonal targets fit into RB tile bits
+    const size_t roundStart = E.rounds.size();
+    unsigned curBits = 0; int curBase = 0, curCount = 0;
+    auto close_round = [&]() {
+        if (!curCount) return;
+        // fill the unused register bits with the highest free tile positions (keeps shared-memory accesses conflict-free)
+        for (int p = T - 1; p >= 0 && __builtin_popcount(curBits) < RB; p--) if (!((curBits >> p) & 1)) curBits |= 1u << p;
+        RoundHdr r; memset(&r, 0, sizeof r);
+        r.kind = ROUND_REG; r.opBase = curBase; r.numOps = curCount;
+        int k = 0, local[TILE_BITS];
+        for (int p = 0; p < T; p++) { local[p] = -1; if ((curBits >> p) & 1) { local[p] = k; r.b[k++] = p; } }
+        for (int o = curBase; o < curBase + curCount; o++) {
+            TileOp& t = E.ops[opStart + o];
+            if (t.kind == OP_DENSE1) t.l0 = local[t.p0];
+            else if (t.kind == OP_SWAP) { t.l0 = std::min(local[t.p0], local[t.p1]); t.l1 = std::max(local[t.p0], local[t.p1]); }
+            else if (t.kind == OP_DENSE2) {
+                int a = local[t.p0], b = local[t.p1];
+                if (a > b) {        // re-order the matrix so that its index bit 0 belongs to the lower register bit
+                    cplx m2[16];
+                    for (int r2 = 0; r2 < 4; r2++) for (int c2 = 0; c2 < 4; c2++) {
+                        int rs = ((r2 & 1) << 1) | (r2 >> 1), cs = ((c2 & 1) << 1) | (c2 >> 1);
+                        m2[4 * rs + cs] = t.m[4 * r2 + c2];
+                    }
+                    for (int i = 0; i < 16; i++) t.m[i] = m2[i];
+                    std::swap(a, b);
+                }
+                t.l0 = a; t.l1 = b;
+            } else if (t.kind == OP_PAULI) {
+                t.lmaskA = t.lmaskB = 0;
+                for (int p = 0; p < T; p++) if (local[p] >= 0) {
+                    if ((t.inMaskA >> p) & 1) t.lmaskA |= 1u << local[p];
+                    if ((t.inMaskB >> p) & 1) t.lmaskB |= 1u << local[p];
+                }
+                t.inMaskB &= ~curBits;          // the kernel adds the round bits' parity through lmaskB
+            }
+        }
+        E.rounds.push_back(r);
+        curBits = 0; curCount = 0;
+    };
+    for (int o = 0; o < h.numOps; o++) {
+        unsigned need = needIn[o];
+        if (E.ops[opStart + o].kind == OP_PAULI && __builtin_popcount(need) > RB) {
+            close_round();
+            RoundHdr r; memset(&r, 0, sizeof r);
+            r.kind = ROUND_SMEM; r.opBase = o; r.numOps = 1;
+            E.rounds.push_back(r);
+            curBase = o + 1;
+            continue;
+        }
+        if (curCount && __builtin_popcount(curBits | need) > RB) close_round();
+        if (!curCount) curBase = o;
+        curBits |= need; curCount++;
+    }
+    close_round();
+    h.numRounds = (int)(E.rounds.size() - roundStart);
+    // opBase inside RoundHdr is relative to the pass's first op
+    E.hdrs.push_back(h);
+    E.opBase.push_back((int)opStart);
+    E.roundBase.push_back((int)roundStart);
 }
 
 static bool is_cphase(const QOp& o) {
@@ -403,10 +583,10 @@ static int flush_queue() {
     // 1. merge ladders of controlled phases that share a qubit into phase stars
     std::vector<QOp> merged;
     for (size_t i = 0; i < ops.size(); ) {
-        if (is_cphase(ops[i]) && ops[i].t0 < n) {
+        if (is_cphase(ops[i])) {
             size_t j = i + 1;
             int a = ops[i].t0, b = __builtin_ctzll(ops[i].ctrlMask), centre = -1;
-            while (j < ops.size() && is_cphase(ops[j]) && ops[j].t0 < n) {
+            while (j < ops.size() && is_cphase(ops[j])) {
                 int c = ops[j].t0, d = __builtin_ctzll(ops[j].ctrlMask);
                 if (centre < 0) { if (c == a || d == a) centre = a; else if (c == b || d == b) centre = b; else break; }
                 else if (c != centre && d != centre) break;
@@ -437,7 +617,7 @@ static int flush_queue() {
         unsigned long long need = nonDiagTargets(merged[i]) & ~lowMask;
         if (merged[i].kind == OP_STAR && merged[i].t0 >= TILE_LOW) need |= 1ULL << merged[i].t0;   // keep the centre in-tile when cheap
         unsigned long long nh = cur.high | need;
-        if (!cur.opIdx.empty() && (__builtin_popcountll(nh) > maxHigh || (int)cur.opIdx.size() >= s_maxOpsPerPass)) {
+        if (!cur.opIdx.empty() && (__builtin_popcountll(nh) > maxHigh || (int)cur.opIdx.size() >= MAX_OPS_PER_PASS)) {
             passes.push_back(cur); cur = Pass(); nh = need;
         }
         if (__builtin_popcountll(nh) > maxHigh) {          // a single op that cannot fit (e.g. Pauli string on > 6 high qubits)
@@ -451,17 +631,17 @@ static int flush_queue() {
     if (!cur.opIdx.empty()) passes.push_back(cur);
 
     // 3. emit: single-op passes use the direct kernels (already at the HBM roofline), multi-op passes the tile kernel
-    std::vector<PassHdr> hdrs; std::vector<TileOp> tops; std::vector<StarTab> tabs; std::vector<int> opCount;
-    std::vector<int> passKind;     // -1: direct op index, else index into hdrs
-    std::vector<int> passArg;
+    Emitted E;
+    std::vector<int> passKind, passArg;     // -1: direct op index, else index into E.hdrs
     for (auto& p : passes) {
         bool direct = (p.high == ~0ULL) || (p.opIdx.size() == 1 && merged[p.opIdx[0]].kind != OP_STAR) || n < TILE_BITS;
         if (direct) { for (int idx : p.opIdx) { passKind.push_back(-1); passArg.push_back(idx); } }
-        else { passKind.push_back((int)hdrs.size()); passArg.push_back(0); emit_pass(&q, merged, p, hdrs, tops, tabs, opCount); }
+        else { passKind.push_back((int)E.hdrs.size()); passArg.push_back(0); emit_pass(&q, merged, p, E); }
     }
-    if (!hdrs.empty()) {
-        size_t bh = hdrs.size() * sizeof(PassHdr), bo = tops.size() * sizeof(TileOp), bt = tabs.size() * sizeof(StarTab);
-        size_t need = bh + bo + bt + 256;
+    const size_t bh = E.hdrs.size() * sizeof(PassHdr), br = E.rounds.size() * sizeof(RoundHdr),
+                 bo = E.ops.size() * sizeof(TileOp), bt = E.tabs.size() * sizeof(StarTab);
+    if (!E.hdrs.empty()) {
+        size_t need = bh + br + bo + bt + 256;
         if (need > s_devDescBytes) {
             cudaStreamSynchronize(g_qb.stream);
             if (s_devDesc) cudaFree(s_devDesc);
@@ -470,32 +650,31 @@ static int flush_queue() {
         }
         if (!rc) {
             // pageable source: the runtime stages the bytes before returning, so the vectors may die right after
-            cudaMemcpyAsync(s_devDesc, hdrs.data(), bh, cudaMemcpyHostToDevice, g_qb.stream);
-            cudaMemcpyAsync(s_devDesc + bh, tops.data(), bo, cudaMemcpyHostToDevice, g_qb.stream);
-            if (bt) cudaMemcpyAsync(s_devDesc + bh + bo, tabs.data(), bt, cudaMemcpyHostToDevice, g_qb.stream);
+            cudaMemcpyAsync(s_devDesc, E.hdrs.data(), bh, cudaMemcpyHostToDevice, g_qb.stream);
+            cudaMemcpyAsync(s_devDesc + bh, E.rounds.data(), br, cudaMemcpyHostToDevice, g_qb.stream);
+            cudaMemcpyAsync(s_devDesc + bh + br, E.ops.data(), bo, cudaMemcpyHostToDevice, g_qb.stream);
+            if (bt) cudaMemcpyAsync(s_devDesc + bh + br + bo, E.tabs.data(), bt, cudaMemcpyHostToDevice, g_qb.stream);
         }
     }
     static bool attrSet = false;
-    const size_t smemBytes = (size_t)TILE_STAGES * TILE_AMPS * sizeof(cplx) + (size_t)s_maxOpsPerPass * sizeof(TileOp);
+    const size_t smemBytes = (size_t)TILE_STAGES * TILE_AMPS * sizeof(cplx) + (size_t)MAX_OPS_PER_PASS * sizeof(TileOp);
     if (!attrSet && !rc) {
         cudaError_t e = cudaFuncSetAttribute(k_tile_pass, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smemBytes);
         if (e != cudaSuccess) rc = qb_set_error((int)e, "cudaFuncSetAttribute(k_tile_pass)", __FILE__, __LINE__);
         attrSet = true;
     }
-    size_t opBase = 0;
     for (size_t i = 0; i < passKind.size() && !rc; i++) {
         if (passKind[i] < 0) { rc = run_direct(&q, merged[passArg[i]]); continue; }
-        int hi = passKind[i];
+        const int hi = passKind[i];
         const PassHdr* dh = (const PassHdr*)s_devDesc + hi;
-        const TileOp* dops = (const TileOp*)(s_devDesc + hdrs.size() * sizeof(PassHdr)) + opBase;
-        const StarTab* dt = (const StarTab*)(s_devDesc + hdrs.size() * sizeof(PassHdr) + tops.size() * sizeof(TileOp));
-        qindex tiles = hdrs[hi].numTiles;
-        unsigned grid = (unsigned)std::min<qindex>(tiles, g_qb.numSMs);
-        k_tile_pass<<<grid, TILE_THREADS, smemBytes, g_qb.stream>>>((cplx*)q.amps, dh, dops, dt);
+        const RoundHdr* dr = (const RoundHdr*)(s_devDesc + bh) + E.roundBase[hi];
+        const TileOp* dops = (const TileOp*)(s_devDesc + bh + br) + E.opBase[hi];
+        const StarTab* dt = (const StarTab*)(s_devDesc + bh + br + bo);
+        unsigned grid = (unsigned)std::min<qindex>(E.hdrs[hi].numTiles, g_qb.numSMs);
+        k_tile_pass<<<grid, TILE_THREADS, smemBytes, g_qb.stream>>>((cplx*)q.amps, dh, dr, dops, dt);
         g_qb.launches++;
         cudaError_t e = cudaGetLastError();
         if (e != cudaSuccess) rc = qb_set_error((int)e, "k_tile_pass launch", __FILE__, __LINE__);
-        opBase += opCount[hi];
     }
     s_inFlush = false;
     if (rc) s_status = rc;
