@@ -17,11 +17,12 @@
 // among the 4 bits (diagonal gates always qualify) and writes the 16 amplitudes back: one shared-memory round trip
 // and one barrier per ROUND instead of per gate.
 //
-// KERNEL.  One persistent CTA per SM (grid = #SMs), 256 threads x 16 amplitudes, 3 stages x 64 KiB of shared memory.
-// Warp 0 also drives the copy engine: cp.async.bulk (TMA, 1-D) loads the chunks of tile k+2 into a free stage,
-// signalling an mbarrier with complete_tx; all threads wait on the stage's mbarrier, run the pass's rounds on the
-// tile, fence.proxy.async, and warp 0 writes the stage back with cp.async.bulk.global.shared::cta (bulk async-groups).
-// Loads of two tiles and the store of one are in flight while a tile is being computed.
+// KERNEL.  One persistent CTA per SM (grid = #SMs): 8 compute warps (256 threads x 16 amplitudes) + 1 copy warp,
+// 3 stages x 64 KiB of shared memory.  The copy warp drives the copy engine: cp.async.bulk (TMA, 1-D) loads the chunks
+// of a tile into a free stage, signalling the stage's `full` mbarrier with complete_tx; the compute warps wait on it,
+// run the pass's rounds on the tile, fence.proxy.async and arrive on the stage's `done` mbarrier; the copy warp then
+// writes the stage back with cp.async.bulk.global.shared::cta (bulk async-groups) and refills it with the tile three
+// ahead.  So while one tile is computed, another is landing and a third is draining: HBM never waits for the SM.
 // Algorithmic bytes per pass: every gate of the pass counts its own 2*16*N/2^c bytes, physical bytes
 // are 2*16*N once per pass (or less: controls shared by every gate of a pass prune whole tiles before they are loaded).
 #include "qb_common.cuh"
@@ -36,7 +37,8 @@
 #define TILE_LOW 6
 #define TILE_AMPS (1 << TILE_BITS)
 #define TILE_STAGES 3
-#define TILE_THREADS 256
+#define TILE_THREADS 256              // compute threads (8 warps); one more warp (the last) only drives the copy engine
+#define TILE_BLOCK (TILE_THREADS + 32)
 #define RB 4                          // tile bits held in registers per round
 #define RAMPS (1 << RB)               // amplitudes per thread: TILE_THREADS * RAMPS == TILE_AMPS
 #define TILE_MAX_CHUNKS (1 << (TILE_BITS - TILE_LOW))
@@ -314,24 +316,30 @@ __device__ __forceinline__ void smem_pauli(cplx* __restrict__ t, const TileOp& o
     }
 }
 
-__global__ void __launch_bounds__(TILE_THREADS, 1) k_tile_pass(cplx* __restrict__ amps, const PassHdr* __restrict__ hdrp,
+__device__ __forceinline__ void mbar_arrive(unsigned long long* bar) {
+    asm volatile("mbarrier.arrive.shared::cta.b64 _, [%0];" :: "r"(smem_u32(bar)) : "memory");
+}
+__device__ __forceinline__ void compute_sync() { asm volatile("bar.sync 1, %0;" :: "n"(TILE_THREADS) : "memory"); }
+
+__global__ void __launch_bounds__(TILE_BLOCK, 1) k_tile_pass(cplx* __restrict__ amps, const PassHdr* __restrict__ hdrp,
         const RoundHdr* __restrict__ grounds, const TileOp* __restrict__ gops, const StarTab* __restrict__ tabs) {
     extern __shared__ __align__(128) unsigned char smem_raw[];
     cplx* stageBuf = reinterpret_cast<cplx*>(smem_raw);                                  // [STAGES][TILE_AMPS]
     TileOp* ops = reinterpret_cast<TileOp*>(smem_raw + (size_t)TILE_STAGES * TILE_AMPS * sizeof(cplx));
-    __shared__ unsigned long long full[TILE_STAGES];
+    __shared__ unsigned long long full[TILE_STAGES];     // copy engine -> compute warps: the tile has landed
+    __shared__ unsigned long long done[TILE_STAGES];     // compute warps -> copy warp: the tile is computed
     __shared__ PassHdr hdr;
     __shared__ RoundHdr rounds[MAX_OPS_PER_PASS];
-    __shared__ cplx starF[MAX_OPS_PER_PASS];
+    __shared__ cplx starF[2][MAX_OPS_PER_PASS];  // double-buffered: a fast warp may start tile k+1 while a slow one finishes tile k
 
     const int tid = threadIdx.x;
-    for (int i = tid; i < (int)(sizeof(PassHdr) / 4); i += TILE_THREADS) ((int*)&hdr)[i] = ((const int*)hdrp)[i];
+    for (int i = tid; i < (int)(sizeof(PassHdr) / 4); i += TILE_BLOCK) ((int*)&hdr)[i] = ((const int*)hdrp)[i];
     __syncthreads();
     const int numOps = hdr.numOps, numRounds = hdr.numRounds;
-    for (int i = tid; i < numOps * (int)(sizeof(TileOp) / 4); i += TILE_THREADS) ((int*)ops)[i] = ((const int*)gops)[i];
-    for (int i = tid; i < numRounds * (int)(sizeof(RoundHdr) / 4); i += TILE_THREADS) ((int*)rounds)[i] = ((const int*)grounds)[i];
+    for (int i = tid; i < numOps * (int)(sizeof(TileOp) / 4); i += TILE_BLOCK) ((int*)ops)[i] = ((const int*)gops)[i];
+    for (int i = tid; i < numRounds * (int)(sizeof(RoundHdr) / 4); i += TILE_BLOCK) ((int*)rounds)[i] = ((const int*)grounds)[i];
     if (tid == 0) {
-        for (int s = 0; s < TILE_STAGES; s++) mbar_init(&full[s], 1);
+        for (int s = 0; s < TILE_STAGES; s++) { mbar_init(&full[s], 1); mbar_init(&done[s], TILE_THREADS / 32); }
         asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
     }
     __syncthreads();
@@ -340,25 +348,40 @@ __global__ void __launch_bounds__(TILE_THREADS, 1) k_tile_pass(cplx* __restrict_
     const int numChunks = hdr.numChunks;
     const unsigned chunkBytes = (unsigned)hdr.chunkAmps * (unsigned)sizeof(cplx);
     const qindex myCount = (numTiles > (qindex)blockIdx.x) ? (numTiles - blockIdx.x + gridDim.x - 1) / gridDim.x : 0;
-
-    // warp 0 drives the copy engine; its 32 lanes share the chunks of a tile so that no single thread serialises
-    // the (up to 64 + 64) bulk-copy issues of a tile while the others wait for it at the next barrier
     const int lane = tid & 31;
-    auto issue_load = [&](qindex k) {          // all lanes of warp 0
-        const int s = (int)(k % TILE_STAGES);
-        const qindex base = hdr.tileIns((qindex)blockIdx.x + k * gridDim.x);
-        if (lane == 0) mbar_expect_tx(&full[s], TILE_AMPS * (unsigned)sizeof(cplx));
-        __syncwarp();
-        cplx* dst = stageBuf + (size_t)s * TILE_AMPS;
-        for (int c = lane; c < numChunks; c += 32)
-            tma_load(dst + (size_t)c * hdr.chunkAmps, amps + base + hdr.chunkOff[c], chunkBytes, &full[s]);
-    };
 
-    if (tid < 32) {
-        if (myCount > 0) issue_load(0);
-        if (myCount > 1) issue_load(1);
+    if (tid >= TILE_THREADS) {
+        // ---------------- copy warp: keeps every stage either loading, being computed, or draining ----------------
+        auto issue_load = [&](qindex k) {
+            const int s = (int)(k % TILE_STAGES);
+            const qindex base = hdr.tileIns((qindex)blockIdx.x + k * gridDim.x);
+            if (lane == 0) mbar_expect_tx(&full[s], TILE_AMPS * (unsigned)sizeof(cplx));
+            __syncwarp();
+            cplx* dst = stageBuf + (size_t)s * TILE_AMPS;
+            for (int c = lane; c < numChunks; c += 32)
+                tma_load(dst + (size_t)c * hdr.chunkAmps, amps + base + hdr.chunkOff[c], chunkBytes, &full[s]);
+        };
+        for (qindex k = 0; k < TILE_STAGES && k < myCount; k++) issue_load(k);
+        for (qindex k = 0; k < myCount; k++) {
+            const int s = (int)(k % TILE_STAGES);
+            const unsigned parity = (unsigned)((k / TILE_STAGES) & 1);
+            const qindex base = hdr.tileIns((qindex)blockIdx.x + k * gridDim.x);
+            cplx* t = stageBuf + (size_t)s * TILE_AMPS;
+            mbar_wait(&done[s], parity);                       // the compute warps fenced their writes before arriving
+            for (int c = lane; c < numChunks; c += 32)
+                tma_store(amps + base + hdr.chunkOff[c], t + (size_t)c * hdr.chunkAmps, chunkBytes);
+            tma_commit();
+            if (k + TILE_STAGES < myCount) {
+                tma_wait_read<0>();                            // the stage may be overwritten once its stores have read it
+                __syncwarp();
+                issue_load(k + TILE_STAGES);
+            }
+        }
+        tma_wait_all<0>();
+        return;
     }
 
+    // ---------------- compute warps ----------------
     for (qindex k = 0; k < myCount; k++) {
         const int s = (int)(k % TILE_STAGES);
         const unsigned parity = (unsigned)((k / TILE_STAGES) & 1);
@@ -371,35 +394,26 @@ __global__ void __launch_bounds__(TILE_THREADS, 1) k_tile_pass(cplx* __restrict_
             cplx f = mk(1, 0);
 #pragma unroll
             for (int sg = 0; sg < STAR_SEGS; sg++) f = cmul(f, __ldg(&tb.ext[sg][(base >> (6 * sg)) & 63]));
-            starF[tid] = f;
+            starF[k & 1][tid] = f;
         }
         mbar_wait(&full[s], parity);
-        __syncthreads();
+        compute_sync();
 
         for (int r = 0; r < numRounds; r++) {
             const RoundHdr& rd = rounds[r];
             if (rd.kind == ROUND_REG) {
-                reg_round(t, rd, ops, base, tabs, starF);
+                reg_round(t, rd, ops, base, tabs, starF[k & 1]);
             } else {
                 const TileOp& op = ops[rd.opBase];
                 if (((unsigned long long)base & op.extCtrlMask) == op.extCtrlVals) smem_pauli(t, op, base);
             }
-            __syncthreads();
+            if (r + 1 < numRounds) compute_sync();
         }
+        // hand the tile to the copy warp: make this warp's shared-memory writes visible to the async proxy, then arrive
         fence_async_smem();
-        __syncthreads();
-        if (tid < 32) {
-            for (int c = lane; c < numChunks; c += 32)
-                tma_store(amps + base + hdr.chunkOff[c], t + (size_t)c * hdr.chunkAmps, chunkBytes);
-            tma_commit();
-            // the stage that tile k+2 will use held tile k-1, whose stores (one bulk group per lane) were
-            // committed one iteration ago: every lane waits for its own, then the warp re-converges
-            tma_wait_read<1>();
-            __syncwarp();
-            if (k + 2 < myCount) issue_load(k + 2);
-        }
+        __syncwarp();
+        if (lane == 0) mbar_arrive(&done[s]);
     }
-    if (tid < 32) tma_wait_all<0>();
 }
 
 // ------------------------------------------------------------------------------------------
@@ -671,7 +685,7 @@ static int flush_queue() {
         const TileOp* dops = (const TileOp*)(s_devDesc + bh + br) + E.opBase[hi];
         const StarTab* dt = (const StarTab*)(s_devDesc + bh + br + bo);
         unsigned grid = (unsigned)std::min<qindex>(E.hdrs[hi].numTiles, g_qb.numSMs);
-        k_tile_pass<<<grid, TILE_THREADS, smemBytes, g_qb.stream>>>((cplx*)q.amps, dh, dr, dops, dt);
+        k_tile_pass<<<grid, TILE_BLOCK, smemBytes, g_qb.stream>>>((cplx*)q.amps, dh, dr, dops, dt);
         g_qb.launches++;
         cudaError_t e = cudaGetLastError();
         if (e != cudaSuccess) rc = qb_set_error((int)e, "k_tile_pass launch", __FILE__, __LINE__);
