@@ -127,7 +127,8 @@ __device__ __forceinline__ cplx csel(bool c, cplx a, cplx b) { return mk(c ? a.x
 // register-round gate bodies: v[u] is the amplitude whose round-bit pattern is u (bit k of u <-> round bit k);
 // `ok` has bit u set when amplitude u satisfies the gate's in-tile controls
 // ------------------------------------------------------------------------------------------
-template <int K>
+// CTRL = false: the gate has no in-tile controls, every amplitude is updated and no selects are emitted
+template <int K, bool CTRL>
 __device__ __forceinline__ void reg_dense1(cplx (&v)[RAMPS], const cplx* __restrict__ m, unsigned ok) {
     const cplx m00 = m[0], m01 = m[1], m10 = m[2], m11 = m[3];
 #pragma unroll
@@ -136,12 +137,12 @@ __device__ __forceinline__ void reg_dense1(cplx (&v)[RAMPS], const cplx* __restr
         const int u1 = u | (1 << K);
         cplx a0 = v[u], a1 = v[u1];
         cplx n0 = cfma(m01, a1, cmul(m00, a0)), n1 = cfma(m11, a1, cmul(m10, a0));
-        const bool c = (ok >> u) & 1;
+        const bool c = CTRL ? (bool)((ok >> u) & 1) : true;
         v[u] = csel(c, n0, a0); v[u1] = csel(c, n1, a1);
     }
 }
 
-template <int K0, int K1>      // K0 < K1; matrix index bit 0 <-> K0, bit 1 <-> K1 (the host re-orders the matrix to make it so)
+template <int K0, int K1, bool CTRL>   // K0 < K1; matrix index bit 0 <-> K0, bit 1 <-> K1 (the host re-orders the matrix to make it so)
 __device__ __forceinline__ void reg_dense2(cplx (&v)[RAMPS], const cplx* __restrict__ mp, unsigned ok) {
     cplx m[16];
 #pragma unroll
@@ -151,7 +152,7 @@ __device__ __forceinline__ void reg_dense2(cplx (&v)[RAMPS], const cplx* __restr
         if (u & ((1 << K0) | (1 << K1))) continue;
         const int i1 = u | (1 << K0), i2 = u | (1 << K1), i3 = i1 | (1 << K1);
         cplx a0 = v[u], a1 = v[i1], a2 = v[i2], a3 = v[i3];
-        const bool c = (ok >> u) & 1;
+        const bool c = CTRL ? (bool)((ok >> u) & 1) : true;
         cplx n0 = cfma(m[3], a3, cfma(m[2], a2, cfma(m[1], a1, cmul(m[0], a0))));
         cplx n1 = cfma(m[7], a3, cfma(m[6], a2, cfma(m[5], a1, cmul(m[4], a0))));
         cplx n2 = cfma(m[11], a3, cfma(m[10], a2, cfma(m[9], a1, cmul(m[8], a0))));
@@ -207,7 +208,8 @@ __device__ __forceinline__ void reg_round(cplx* __restrict__ t, const RoundHdr& 
         const TileOp& op = ops[rd.opBase + o];
         if (((unsigned long long)base & op.extCtrlMask) != op.extCtrlVals) continue;      // tile-uniform
         unsigned ok = 0xFFFFu;
-        if (op.inCtrlMask) {
+        const bool nc = op.inCtrlMask == 0;
+        if (!nc) {
             ok = 0;
 #pragma unroll
             for (int u = 0; u < RAMPS; u++) ok |= (unsigned)(((jb | OFF(u)) & op.inCtrlMask) == op.inCtrlVals) << u;
@@ -215,20 +217,20 @@ __device__ __forceinline__ void reg_round(cplx* __restrict__ t, const RoundHdr& 
         switch (op.kind) {
         case OP_DENSE1:
             switch (op.l0) {
-            case 0: reg_dense1<0>(v, op.m, ok); break;
-            case 1: reg_dense1<1>(v, op.m, ok); break;
-            case 2: reg_dense1<2>(v, op.m, ok); break;
-            default: reg_dense1<3>(v, op.m, ok); break;
+            case 0: if (nc) reg_dense1<0, false>(v, op.m, ok); else reg_dense1<0, true>(v, op.m, ok); break;
+            case 1: if (nc) reg_dense1<1, false>(v, op.m, ok); else reg_dense1<1, true>(v, op.m, ok); break;
+            case 2: if (nc) reg_dense1<2, false>(v, op.m, ok); else reg_dense1<2, true>(v, op.m, ok); break;
+            default: if (nc) reg_dense1<3, false>(v, op.m, ok); else reg_dense1<3, true>(v, op.m, ok); break;
             }
             break;
         case OP_DENSE2:
             switch (op.l0 * 4 + op.l1) {
-            case 1: reg_dense2<0, 1>(v, op.m, ok); break;
-            case 2: reg_dense2<0, 2>(v, op.m, ok); break;
-            case 3: reg_dense2<0, 3>(v, op.m, ok); break;
-            case 6: reg_dense2<1, 2>(v, op.m, ok); break;
-            case 7: reg_dense2<1, 3>(v, op.m, ok); break;
-            default: reg_dense2<2, 3>(v, op.m, ok); break;
+            case 1: if (nc) reg_dense2<0, 1, false>(v, op.m, ok); else reg_dense2<0, 1, true>(v, op.m, ok); break;
+            case 2: if (nc) reg_dense2<0, 2, false>(v, op.m, ok); else reg_dense2<0, 2, true>(v, op.m, ok); break;
+            case 3: if (nc) reg_dense2<0, 3, false>(v, op.m, ok); else reg_dense2<0, 3, true>(v, op.m, ok); break;
+            case 6: if (nc) reg_dense2<1, 2, false>(v, op.m, ok); else reg_dense2<1, 2, true>(v, op.m, ok); break;
+            case 7: if (nc) reg_dense2<1, 3, false>(v, op.m, ok); else reg_dense2<1, 3, true>(v, op.m, ok); break;
+            default: if (nc) reg_dense2<2, 3, false>(v, op.m, ok); else reg_dense2<2, 3, true>(v, op.m, ok); break;
             }
             break;
         case OP_SWAP:
@@ -278,15 +280,18 @@ __device__ __forceinline__ void reg_round(cplx* __restrict__ t, const RoundHdr& 
         } break;
         case OP_STAR: {
             // amplitudes with centre bit 1 gain exp(i sum_c theta_c bit_c): product of per-segment table entries
+            // phase(j) is additive over the bits of j, so it splits into a per-thread factor (tile bits outside the
+            // round, via the two 64-entry tables, times the per-tile external factor) and a per-register factor
+            // op.m[u] (the round's own bits; identical for every thread, precomputed on the host)
             const StarTab& tb = tabs[op.tab];
             if (op.p0 < 0 && !getBit(base, op.e0)) break;
-            const cplx f = starF[rd.opBase + o];
+            const cplx eb = cmul(cmul(__ldg(&tb.in[0][jb & 63]), __ldg(&tb.in[1][jb >> 6])), starF[rd.opBase + o]);
+            const bool fixedOn = (op.p0 < 0) || (op.l0 < 0 && ((jb >> op.p0) & 1));
+            if (op.l0 < 0 && !fixedOn) break;          // centre is a non-round tile bit that is 0 for this thread
 #pragma unroll
             for (int u = 0; u < RAMPS; u++) {
-                const unsigned j = jb | OFF(u);
-                const bool on = (op.p0 < 0) ? true : ((j >> op.p0) & 1);
-                cplx e = cmul(cmul(__ldg(&tb.in[0][j & 63]), __ldg(&tb.in[1][j >> 6])), f);
-                v[u] = csel(on, cmul(v[u], e), v[u]);
+                const bool on = (op.l0 < 0) ? true : ((u >> op.l0) & 1);
+                v[u] = csel(on, cmul(v[u], cmul(eb, op.m[u])), v[u]);
             }
         } break;
         }
@@ -542,6 +547,17 @@ static void emit_pass(const qb_state* q, const std::vector<QOp>& ops, const Pass
                     std::swap(a, b);
                 }
                 t.l0 = a; t.l1 = b;
+            } else if (t.kind == OP_STAR) {
+                // per-register phase factors over the round's own bits; the tables keep every other bit
+                const QOp& qo = ops[pass.opIdx[o]];
+                t.l0 = (t.p0 >= 0) ? local[t.p0] : -1;
+                long double ang[RAMPS] = {0};
+                for (auto& ce : qo.star) {
+                    int p = pos[ce.first];
+                    if (p >= 0 && local[p] >= 0)
+                        for (int u = 0; u < RAMPS; u++) if ((u >> local[p]) & 1) ang[u] += ce.second;
+                }
+                for (int u = 0; u < RAMPS; u++) t.m[u] = mk((double)cosl(ang[u]), (double)sinl(ang[u]));
             } else if (t.kind == OP_PAULI) {
                 t.lmaskA = t.lmaskB = 0;
                 for (int p = 0; p < T; p++) if (local[p] >= 0) {
