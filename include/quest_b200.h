@@ -79,7 +79,7 @@ qb_cplx*    qb_get_cache(qb_index numElems, int* status);/* gpu_getCacheOfSize  
 int         qb_clear_cache(void);                        /* gpu_clearCache             gpu_config.cpp:665 */
 size_t      qb_cache_bytes(void);                        /* gpu_getCacheMemoryInBytes  gpu_config.cpp:683 */
 unsigned long long qb_launch_count(void);                /* kernels launched by this library so far */
-int         qb_set_tile_engine(int enabled);             /* 1 (default): TMA tile kernels where applicable; 0: direct kernels only */
+int         qb_set_tile_engine(int enabled);             /* 1 (default): fused TMA tile passes (gate absorption + commuting re-order); 2: fused, program order; 0: direct kernels only */
 int         qb_selftest_bitins(const int* qubits, const int* states, int n, qb_index item, qb_index* out); /* host-only index-algebra check */
 
 /* ------------------------------------------------------------------------------------------

@@ -24,7 +24,7 @@ struct QbRuntime {
     int numSMs = 148;
     cudaStream_t stream = 0;     // all compute goes here (default: legacy stream 0)
     unsigned long long launches = 0;
-    bool tileEngine = true;
+    int tileEngine = 1;          // 0: direct kernels only; 1: fused passes with gate absorption + commuting re-order; 2: fused, program order
     // reduction scratch (device) + pinned host landing zone
     double* redPartials = nullptr;   // [QB_RED_MAX_BLOCKS * 2 * QB_RED_MAX_OUT]
     unsigned int* redTicket = nullptr;

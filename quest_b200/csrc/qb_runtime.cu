@@ -255,7 +255,7 @@ unsigned long long qb_launch_count(void) { return g_qb.launches; }
 
 int qb_set_tile_engine(int enabled) {
     if (g_qb.device >= 0) QB_FLUSH();
-    g_qb.tileEngine = enabled != 0;
+    g_qb.tileEngine = (enabled < 0 || enabled > 2) ? 1 : enabled;
     return 0;
 }
 

@@ -435,6 +435,99 @@ static inline unsigned long long nonDiagTargets(const QOp& o) {
     }
 }
 
+// qubits an op involves only DIAGONALLY (controls, diagonal targets, Z sites, phase-star members): two ops commute
+// unless one's non-diagonal targets meet any qubit of the other
+static inline unsigned long long diagQubits(const QOp& o) {
+    unsigned long long d = o.ctrlMask;
+    switch (o.kind) {
+    case OP_PAULI: d |= o.maskB & ~o.maskA; break;
+    case OP_DIAG: d |= 1ULL << o.t0; if (o.numT > 1) d |= 1ULL << o.t1; break;
+    case OP_PARITY: d |= o.maskA; break;
+    case OP_STAR: d |= 1ULL << o.t0; for (auto& ce : o.star) d |= 1ULL << ce.first; break;
+    default: break;
+    }
+    return d;
+}
+
+// first-fit list scheduling shared by the pass and the round planners: walk `cand` in program order, take an op when
+// `fits(op)` accepts it and it commutes with every op skipped so far; skipped ops block their qubits.  Taken ops keep
+// their relative order, and each one only moves ahead of ops it commutes with, so the product is unchanged.
+template <class Fits>
+static void first_fit(const std::vector<QOp>& ops, const std::vector<int>& cand, size_t maxTake, Fits fits,
+                      std::vector<int>& taken, std::vector<int>& rest) {
+    unsigned long long blockedND = 0, blockedAny = 0;
+    for (size_t i = 0; i < cand.size(); i++) {
+        const QOp& o = ops[cand[i]];
+        const unsigned long long nd = nonDiagTargets(o), dg = diagQubits(o);
+        const bool free = !(nd & blockedAny) && !(dg & blockedND);
+        if (free && taken.size() < maxTake && fits(o, taken.empty())) taken.push_back(cand[i]);
+        else { blockedND |= nd; blockedAny |= nd | dg; rest.push_back(cand[i]); }
+    }
+}
+
+static inline cplx hmul(cplx a, cplx b) { return mk(a.x * b.x - a.y * b.y, a.x * b.y + a.y * b.x); }
+
+// 4x4 product helpers for gate absorption; matrices are row-major, index bit 0 <-> t0, bit 1 <-> t1
+static void embed1(const cplx* u, int slot, cplx* e) {       // e = u acting on index bit `slot`, identity on the other
+    for (int r = 0; r < 4; r++) for (int c = 0; c < 4; c++) {
+        const int rs = (r >> slot) & 1, cs = (c >> slot) & 1, ro = (r >> (1 - slot)) & 1, co = (c >> (1 - slot)) & 1;
+        e[4 * r + c] = (ro == co) ? u[2 * rs + cs] : mk(0, 0);
+    }
+}
+static void matmul(const cplx* a, const cplx* b, int d, cplx* out) {      // out = a * b (d x d)
+    cplx t[16];
+    for (int r = 0; r < d; r++) for (int c = 0; c < d; c++) {
+        cplx s = mk(0, 0);
+        for (int k = 0; k < d; k++) { cplx p = hmul(a[d * r + k], b[d * k + c]); s.x += p.x; s.y += p.y; }
+        t[d * r + c] = s;
+    }
+    for (int i = 0; i < d * d; i++) out[i] = t[i];
+}
+
+// Gate absorption: a control-free 1-qubit dense gate is multiplied into the neighbouring control-free dense gate on
+// the same qubit (the previous one if that is the last op touching the qubit, else the next 2-qubit gate that finds it
+// still "open"), and consecutive 2-qubit gates on the same pair are multiplied together.  Host-side 2x2 / 4x4 products;
+// the amplitudes then see one gate instead of two.
+static void absorb_gates(std::vector<QOp>& ops) {
+    std::vector<char> dead(ops.size(), 0);
+    int last[64];
+    for (int b = 0; b < 64; b++) last[b] = -1;
+    auto plain = [&](int i, int kind) { return i >= 0 && !dead[i] && ops[i].kind == kind && ops[i].ctrlMask == 0; };
+    for (size_t i = 0; i < ops.size(); i++) {
+        QOp& o = ops[i];
+        if (o.kind == OP_DENSE1 && o.ctrlMask == 0) {
+            const int p = last[o.t0];
+            if (plain(p, OP_DENSE1)) { matmul(o.m, ops[p].m, 2, ops[p].m); ops[p].algBytes += o.algBytes; dead[i] = 1; continue; }
+            if (plain(p, OP_DENSE2)) {
+                cplx e[16]; embed1(o.m, ops[p].t0 == o.t0 ? 0 : 1, e);
+                matmul(e, ops[p].m, 4, ops[p].m); ops[p].algBytes += o.algBytes; dead[i] = 1; continue;
+            }
+        } else if (o.kind == OP_DENSE2 && o.ctrlMask == 0) {
+            const int pa = last[o.t0], pb = last[o.t1];
+            if (pa == pb && plain(pa, OP_DENSE2)) {          // same pair (either order): multiply into the earlier gate
+                QOp& e = ops[pa];
+                cplx m2[16];
+                const bool flip = e.t0 != o.t0;
+                for (int r = 0; r < 4; r++) for (int c = 0; c < 4; c++) {
+                    const int rs = flip ? (((r & 1) << 1) | (r >> 1)) : r, cs = flip ? (((c & 1) << 1) | (c >> 1)) : c;
+                    m2[4 * rs + cs] = o.m[4 * r + c];
+                }
+                matmul(m2, e.m, 4, e.m); e.algBytes += o.algBytes; dead[i] = 1; continue;
+            }
+            const int tq[2] = {o.t0, o.t1};
+            for (int s = 0; s < 2; s++) {
+                const int p = last[tq[s]];
+                if (plain(p, OP_DENSE1)) { cplx e[16]; embed1(ops[p].m, s, e); matmul(o.m, e, 4, o.m); o.algBytes += ops[p].algBytes; dead[p] = 1; }
+            }
+        }
+        unsigned long long all = nonDiagTargets(o) | diagQubits(o);
+        for (int b = 0; b < 64; b++) if ((all >> b) & 1) last[b] = (int)i;
+    }
+    size_t w = 0;
+    for (size_t i = 0; i < ops.size(); i++) if (!dead[i]) { if (w != i) ops[w] = ops[i]; w++; }
+    ops.resize(w);
+}
+
 static int run_direct(const qb_state* q, const QOp& o);
 
 struct Emitted {
@@ -442,7 +535,7 @@ struct Emitted {
     std::vector<int> opBase, roundBase;
 };
 
-static void emit_pass(const qb_state* q, const std::vector<QOp>& ops, const Pass& pass, Emitted& E) {
+static void emit_pass(const qb_state* q, const std::vector<QOp>& ops, const Pass& pass, Emitted& E, bool reorder) {
     const int n = q->logNumAmpsPerNode;
     // tile bit set S: the low bits, the required high bits, then filler (lowest unused bits) up to TILE_BITS
     unsigned long long S = ((1ULL << TILE_LOW) - 1) | pass.high;
@@ -479,8 +572,40 @@ static void emit_pass(const qb_state* q, const std::vector<QOp>& ops, const Pass
 
     auto toIn = [&](unsigned long long gm) { unsigned v = 0; for (int p = 0; p < T; p++) if ((gm >> sbits[p]) & 1) v |= 1u << p; return v; };
     const size_t opStart = E.ops.size();
+
+    // rounds: first-fit again, now over the pass's ops -- a round takes every op whose non-diagonal targets still fit
+    // into its RB register bits and that commutes with the ops it overtakes.  `order` lists the pass's ops round by round.
+    std::vector<int> order, roundLen, roundKind;
+    {
+        std::vector<int> remaining = pass.opIdx;
+        while (!remaining.empty()) {
+            const QOp& first = ops[remaining[0]];
+            if (first.kind == OP_PAULI && __builtin_popcount(toIn(first.maskA)) > RB) {      // shared-memory round of its own
+                order.push_back(remaining[0]); roundLen.push_back(1); roundKind.push_back(ROUND_SMEM);
+                remaining.erase(remaining.begin());
+                continue;
+            }
+            std::vector<int> taken, rest;
+            unsigned bits = 0;
+            first_fit(ops, remaining, 1000000, [&](const QOp& o, bool) {
+                const unsigned nb = bits | toIn(nonDiagTargets(o));
+                if (__builtin_popcount(nb) > RB) return false;
+                bits = nb; return true;
+            }, taken, rest);
+            if (!reorder) {
+                size_t keep = 0;
+                while (keep < taken.size() && taken[keep] == remaining[keep]) keep++;
+                taken.resize(keep);
+                rest.assign(remaining.begin() + keep, remaining.end());
+            }
+            for (int idx : taken) order.push_back(idx);
+            roundLen.push_back((int)taken.size()); roundKind.push_back(ROUND_REG);
+            remaining.swap(rest);
+        }
+    }
+
     std::vector<unsigned> needIn;            // per op: tile-bit positions its non-diagonal targets occupy
-    for (int idx : pass.opIdx) {
+    for (int idx : order) {
         const QOp& o = ops[idx];
         TileOp t; memset(&t, 0, sizeof t);
         t.kind = o.kind; t.numT = o.numT;
@@ -520,7 +645,7 @@ static void emit_pass(const qb_state* q, const std::vector<QOp>& ops, const Pass
         E.ops.push_back(t);
     }
 
-    // rounds: greedily pack consecutive ops whose non-diagonal targets fit into RB tile bits
+    // per-round register bits and the ops' coordinates relative to them
     const size_t roundStart = E.rounds.size();
     unsigned curBits = 0; int curBase = 0, curCount = 0;
     auto close_round = [&]() {
@@ -549,7 +674,7 @@ static void emit_pass(const qb_state* q, const std::vector<QOp>& ops, const Pass
                 t.l0 = a; t.l1 = b;
             } else if (t.kind == OP_STAR) {
                 // per-register phase factors over the round's own bits; the tables keep every other bit
-                const QOp& qo = ops[pass.opIdx[o]];
+                const QOp& qo = ops[order[o]];
                 t.l0 = (t.p0 >= 0) ? local[t.p0] : -1;
                 long double ang[RAMPS] = {0};
                 for (auto& ce : qo.star) {
@@ -570,21 +695,17 @@ static void emit_pass(const qb_state* q, const std::vector<QOp>& ops, const Pass
         E.rounds.push_back(r);
         curBits = 0; curCount = 0;
     };
-    for (int o = 0; o < h.numOps; o++) {
-        unsigned need = needIn[o];
-        if (E.ops[opStart + o].kind == OP_PAULI && __builtin_popcount(need) > RB) {
-            close_round();
-            RoundHdr r; memset(&r, 0, sizeof r);
-            r.kind = ROUND_SMEM; r.opBase = o; r.numOps = 1;
-            E.rounds.push_back(r);
-            curBase = o + 1;
+    for (size_t r = 0, o = 0; r < roundLen.size(); o += roundLen[r], r++) {
+        if (roundKind[r] == ROUND_SMEM) {
+            RoundHdr rh; memset(&rh, 0, sizeof rh);
+            rh.kind = ROUND_SMEM; rh.opBase = (int)o; rh.numOps = 1;
+            E.rounds.push_back(rh);
             continue;
         }
-        if (curCount && __builtin_popcount(curBits | need) > RB) close_round();
-        if (!curCount) curBase = o;
-        curBits |= need; curCount++;
+        curBase = (int)o; curCount = roundLen[r]; curBits = 0;
+        for (int k = 0; k < curCount; k++) curBits |= needIn[o + k];
+        close_round();
     }
-    close_round();
     h.numRounds = (int)(E.rounds.size() - roundStart);
     // opBase inside RoundHdr is relative to the pass's first op
     E.hdrs.push_back(h);
@@ -609,6 +730,8 @@ static int flush_queue() {
     qb_state q = s_qstate; s_qvalid = false;
     const int n = q.logNumAmpsPerNode;
     int rc = 0;
+    const bool reorder = g_qb.tileEngine != 2;
+    if (reorder) absorb_gates(ops);
 
     // 1. merge ladders of controlled phases that share a qubit into phase stars
     std::vector<QOp> merged;
@@ -638,27 +761,43 @@ static int flush_queue() {
         merged.push_back(ops[i++]);
     }
 
-    // 2. greedy grouping into passes
+    // 2. grouping into passes: first-fit over the whole queue -- a pass takes every op (in program order) whose high
+    //    non-diagonal targets still fit into its six free tile bits and that commutes with everything it overtakes
     std::vector<Pass> passes;
-    Pass cur;
     const int maxHigh = TILE_BITS - TILE_LOW;
     const unsigned long long lowMask = (1ULL << TILE_LOW) - 1;
-    for (size_t i = 0; i < merged.size(); i++) {
-        unsigned long long need = nonDiagTargets(merged[i]) & ~lowMask;
-        if (merged[i].kind == OP_STAR && merged[i].t0 >= TILE_LOW) need |= 1ULL << merged[i].t0;   // keep the centre in-tile when cheap
-        unsigned long long nh = cur.high | need;
-        if (!cur.opIdx.empty() && (__builtin_popcountll(nh) > maxHigh || (int)cur.opIdx.size() >= MAX_OPS_PER_PASS)) {
-            passes.push_back(cur); cur = Pass(); nh = need;
-        }
-        if (__builtin_popcountll(nh) > maxHigh) {          // a single op that cannot fit (e.g. Pauli string on > 6 high qubits)
-            if (!cur.opIdx.empty()) { passes.push_back(cur); cur = Pass(); }
-            Pass solo; solo.opIdx.push_back((int)i); solo.high = ~0ULL;   // marker: run direct
-            passes.push_back(solo);
+    auto highNeed = [&](const QOp& o) {
+        unsigned long long need = nonDiagTargets(o) & ~lowMask;
+        if (o.kind == OP_STAR && o.t0 >= TILE_LOW) need |= 1ULL << o.t0;       // keep the centre in-tile when cheap
+        return need;
+    };
+    std::vector<int> remaining(merged.size());
+    for (size_t i = 0; i < merged.size(); i++) remaining[i] = (int)i;
+    while (!remaining.empty()) {
+        Pass cur;
+        if (__builtin_popcountll(highNeed(merged[remaining[0]])) > maxHigh) {   // cannot fit any tile (e.g. Pauli string on > 6 high qubits)
+            cur.opIdx.push_back(remaining[0]); cur.high = ~0ULL;                // marker: run direct
+            remaining.erase(remaining.begin());
+            passes.push_back(cur);
             continue;
         }
-        cur.high = nh; cur.opIdx.push_back((int)i);
+        std::vector<int> rest;
+        first_fit(merged, remaining, reorder ? MAX_OPS_PER_PASS : 1000000, [&](const QOp& o, bool) {
+            const unsigned long long nh = cur.high | highNeed(o);
+            if (__builtin_popcountll(nh) > maxHigh) return false;
+            cur.high = nh; return true;
+        }, cur.opIdx, rest);
+        if (!reorder) {
+            // program order only: cut the pass at the first op that did not fit
+            size_t keep = 0;
+            while (keep < cur.opIdx.size() && cur.opIdx[keep] == remaining[keep] && keep < MAX_OPS_PER_PASS) keep++;
+            cur.opIdx.resize(keep); cur.high = 0;
+            for (int idx : cur.opIdx) cur.high |= highNeed(merged[idx]);
+            rest.assign(remaining.begin() + keep, remaining.end());
+        }
+        remaining.swap(rest);
+        passes.push_back(cur);
     }
-    if (!cur.opIdx.empty()) passes.push_back(cur);
 
     // 3. emit: single-op passes use the direct kernels (already at the HBM roofline), multi-op passes the tile kernel
     Emitted E;
@@ -666,7 +805,7 @@ static int flush_queue() {
     for (auto& p : passes) {
         bool direct = (p.high == ~0ULL) || (p.opIdx.size() == 1 && merged[p.opIdx[0]].kind != OP_STAR) || n < TILE_BITS;
         if (direct) { for (int idx : p.opIdx) { passKind.push_back(-1); passArg.push_back(idx); } }
-        else { passKind.push_back((int)E.hdrs.size()); passArg.push_back(0); emit_pass(&q, merged, p, E); }
+        else { passKind.push_back((int)E.hdrs.size()); passArg.push_back(0); emit_pass(&q, merged, p, E, reorder); }
     }
     const size_t bh = E.hdrs.size() * sizeof(PassHdr), br = E.rounds.size() * sizeof(RoundHdr),
                  bo = E.ops.size() * sizeof(TileOp), bt = E.tabs.size() * sizeof(StarTab);

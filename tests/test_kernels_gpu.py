@@ -581,6 +581,37 @@ def test_fused_gate_sequences(n, rank, logNodes):
         assert launches < nops, f"no fusion happened: {launches} launches for {nops} gates"
 
 
+@pytest.mark.parametrize("mode", [1, 2], ids=["absorb+reorder", "program-order"])
+@pytest.mark.parametrize("n,span", [(13, 4), (16, 16), (20, 7), (22, 22)])
+def test_fused_dense_streams(n, span, mode):
+    """bench-like streams of control-free dense 1/2-qubit gates (here crowded onto `span` qubits so that nearly every
+    gate has a neighbour to be multiplied into), salted with controlled and diagonal gates that must block absorption
+    and re-ordering across them: planner mode 1 (gate absorption + commuting re-order) and mode 2 (program order)"""
+    capi.call("qb_set_tile_engine", mode)
+    rng = np.random.default_rng(1700 + n + span)
+    qubits = [int(q) for q in rng.choice(n, size=span, replace=False)]
+    st = rand_sv(rng, n); dev = Dev(st)
+    launches0 = capi.lib().qb_launch_count()
+    nops = 150
+    for _ in range(nops):
+        r = rng.integers(10)
+        if r < 4:
+            t = int(rng.choice(qubits)); m = rand_unitary(rng, 2)
+            capi.call("qb_statevec_anyCtrlOneTargDenseMatr_subA", dev.ref, capi.ints([]), capi.ints([]), 0, t, capi.cplx_array(m))
+            qo.statevec_anyCtrlOneTargDenseMatr_subA(st, [], [], t, m)
+        elif r < 8:
+            t = [int(q) for q in rng.choice(qubits, size=2, replace=False)]; m = rand_unitary(rng, 4)
+            capi.call("qb_statevec_anyCtrlTwoTargDenseMatr_sub", dev.ref, capi.ints([]), capi.ints([]), 0, t[0], t[1], capi.cplx_array(m))
+            qo.statevec_anyCtrlTwoTargDenseMatr_sub(st, [], [], t[0], t[1], m)
+        else:
+            _random_fusable_op(rng, n, st, dev)
+    err = rel_l2(dev.host(), st.amps)
+    launches = capi.lib().qb_launch_count() - launches0
+    capi.call("qb_set_tile_engine", 1)
+    assert err <= TOL * 5, f"dense stream n={n} span={span} mode={mode}: rel-L2 {err:.3e}"
+    assert launches < nops // 2
+
+
 @pytest.mark.parametrize("n", [13, 18, 21])
 def test_fused_qft_matches_gate_by_gate(n):
     """the QFT ladder (api/operations.cpp:1934-1953) through the phase-star merge vs the same gates one at a time"""

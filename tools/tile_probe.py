@@ -32,7 +32,7 @@ def run(label, gates, reps=5):
     ms = e0.elapsed_time(e1) / reps
     print(f"{label:58s} gates={len(gates):3d} launches={launches:5.1f} ms={ms:8.3f} ms/launch={ms/launches:7.3f}", flush=True)
 
-capi.call("qb_set_tile_engine", 1)
+capi.call("qb_set_tile_engine", 2)      # program order, no gate absorption: the probe repeats gates on purpose
 hb = [26, 27, 28, 29]
 run("4xH on q26..29 (1 round, 16 chunks)", [("h", q) for q in hb])
 run("8xH on q26..29 x2 (1 round)", [("h", q) for q in hb * 2])
@@ -44,6 +44,10 @@ run("8xH: q26..29 then q2..5 (2 rounds, 2-way conflicts)", [("h", q) for q in hb
 run("8xH: q26..29 then q0..3 (2 rounds, 8-way conflicts)", [("h", q) for q in hb + [0, 1, 2, 3]])
 run("2x m2 (26,27),(28,29) (1 round)", [("m2", 26, 27), ("m2", 28, 29)])
 run("4x m2 same x2 (1 round)", [("m2", 26, 27), ("m2", 28, 29)] * 2)
+run("8x m2 same x4 (1 round)", [("m2", 26, 27), ("m2", 28, 29)] * 4)
+run("6xH: q26..29 then q6,q7 (2 rounds, no conflicts)", [("h", q) for q in hb + [6, 7]])
+run("10xH: q26..29, q6,q7, q26..29 (3 rounds, no conflicts)", [("h", q) for q in hb + [6, 7] + hb])
+run("6xH: q26..29 then q4,q5 (2 rounds)", [("h", q) for q in hb + [4, 5]])
 run("6xH on q24..q29 (2 rounds, 64 chunks of 1 KiB)", [("h", q) for q in range(24, 30)])
 run("QFT block: H29 + 29 cphase + H28 + 28 cphase", [("h", 29)] + [("cp", 29, c) for c in range(29)] + [("h", 28)] + [("cp", 28, c) for c in range(28)])
 capi.call("qb_set_tile_engine", 0)
