@@ -17,7 +17,8 @@
 // among the 4 bits (diagonal gates always qualify) and writes the 16 amplitudes back: one shared-memory round trip
 // and one barrier per ROUND instead of per gate.
 //
-// KERNEL.  One persistent CTA per SM (grid = #SMs): 8 compute warps (256 threads x 16 amplitudes) + 1 copy warp,
+// KERNEL.  One persistent CTA per SM (grid = #SMs): 8 compute warps (256 threads x 16 amplitudes, 232 registers each
+// after setmaxnreg) + 1 copy warp (its warpgroup gives its registers away),
 // 3 stages x 64 KiB of shared memory.  The copy warp drives the copy engine: cp.async.bulk (TMA, 1-D) loads the chunks
 // of a tile into a free stage, signalling the stage's `full` mbarrier with complete_tx; the compute warps wait on it,
 // run the pass's rounds on the tile, fence.proxy.async and arrive on the stage's `done` mbarrier; the copy warp then
@@ -29,6 +30,7 @@
 #include "qb_kernels.cuh"
 #include "qb_tile.cuh"
 #include <math.h>
+#include <stddef.h>
 #include <string.h>
 #include <vector>
 #include <algorithm>
@@ -38,7 +40,9 @@
 #define TILE_AMPS (1 << TILE_BITS)
 #define TILE_STAGES 3
 #define TILE_THREADS 256              // compute threads (8 warps); one more warp (the last) only drives the copy engine
-#define TILE_BLOCK (TILE_THREADS + 32)
+#define TILE_BLOCK (TILE_THREADS + 128)  // + one warpgroup whose first warp is the copy warp (register re-allocation is per warpgroup)
+#define COMPUTE_REGS 232              // setmaxnreg: 384 x 168 at launch -> 256 x 232 (compute) + 128 x 40 (copy warpgroup)
+#define COPY_REGS 40
 #define RB 4                          // tile bits held in registers per round
 #define RAMPS (1 << RB)               // amplitudes per thread: TILE_THREADS * RAMPS == TILE_AMPS
 #define TILE_MAX_CHUNKS (1 << (TILE_BITS - TILE_LOW))
@@ -71,17 +75,28 @@ static bool s_inFlush = false;
 
 // device-side op, in tile coordinates
 struct TileOp {
-    int kind, p0, p1, numT;                    // in-tile positions (p < 0: target outside the tile, diag/star only)
+    // quad 0: everything the round's dispatcher needs, fetched with one 128-bit shared-memory load (and prefetched
+    // one op ahead): `code` selects the fully specialised gate body (see op_code)
+    int code, kind;
+    unsigned int inCtrlMask, inCtrlVals;
+    int p0, p1, numT, tab;                     // in-tile positions (p < 0: target outside the tile, diag/star only); OP_STAR: table block
     int e0, e1;                                // global bit index of an external diag target / star centre
     int l0, l1;                                // register rounds: index (0..3) of the target bits among the round's bits
     unsigned int lmaskA, lmaskB;               // register rounds: pauli XY mask / YZ-or-parity mask over the round's bits
-    unsigned int inCtrlMask, inCtrlVals;
     unsigned int inMaskA, inMaskB;             // pauli XY / YZ (or parity) masks over the 12 tile bits
     unsigned long long extCtrlMask, extCtrlVals;
-    unsigned long long extMaskB;               // pauli / parity: sign bits outside the tile
-    int tab, pad;                              // OP_STAR: index of its table block
+    unsigned long long extMaskB, pad;          // pauli / parity: sign bits outside the tile
     cplx m[16];
 };
+static_assert(sizeof(TileOp) % 16 == 0 && offsetof(TileOp, m) % 16 == 0, "TileOp is read with 128-bit loads");
+
+// dispatch codes: one per specialised body
+enum { CODE_DENSE1 = 0,      // + 2 * l0 + hasInTileCtrl                (8)
+       CODE_DENSE2 = 8,      // + 2 * pairIndex(l0, l1) + hasInTileCtrl (12)
+       CODE_SWAP = 20,       // + pairIndex                             (6)
+       CODE_PAULI = 26,      // + lmaskA - 1                            (15)
+       CODE_DIAG = 41, CODE_PARITY = 42, CODE_STAR = 43 };
+static inline int pair_index(int a, int b) { return a == 0 ? b - 1 : (a == 1 ? b + 1 : 5); }   // (0,1)(0,2)(0,3)(1,2)(1,3)(2,3) -> 0..5
 
 struct RoundHdr { int kind, opBase, numOps, pad; int b[RB]; };
 struct StarTab { cplx in[2][64]; cplx ext[STAR_SEGS][64]; };
@@ -129,8 +144,7 @@ __device__ __forceinline__ cplx csel(bool c, cplx a, cplx b) { return mk(c ? a.x
 // ------------------------------------------------------------------------------------------
 // CTRL = false: the gate has no in-tile controls, every amplitude is updated and no selects are emitted
 template <int K, bool CTRL>
-__device__ __forceinline__ void reg_dense1(cplx (&v)[RAMPS], const cplx* __restrict__ m, unsigned ok) {
-    const cplx m00 = m[0], m01 = m[1], m10 = m[2], m11 = m[3];
+__device__ __forceinline__ void reg_dense1(cplx (&v)[RAMPS], cplx m00, cplx m01, cplx m10, cplx m11, unsigned ok) {
 #pragma unroll
     for (int u = 0; u < RAMPS; u++) {
         if (u & (1 << K)) continue;
@@ -142,11 +156,14 @@ __device__ __forceinline__ void reg_dense1(cplx (&v)[RAMPS], const cplx* __restr
     }
 }
 
-template <int K0, int K1, bool CTRL>   // K0 < K1; matrix index bit 0 <-> K0, bit 1 <-> K1 (the host re-orders the matrix to make it so)
-__device__ __forceinline__ void reg_dense2(cplx (&v)[RAMPS], const cplx* __restrict__ mp, unsigned ok) {
+// K0 < K1; matrix index bit 0 <-> K0, bit 1 <-> K1 (the host re-orders the matrix to make it so); the first matrix row
+// arrives in registers (prefetched while the previous gate ran), the other three are loaded while it is being used
+template <int K0, int K1, bool CTRL>
+__device__ __forceinline__ void reg_dense2(cplx (&v)[RAMPS], cplx r0, cplx r1, cplx r2, cplx r3, const cplx* __restrict__ mp, unsigned ok) {
     cplx m[16];
+    m[0] = r0; m[1] = r1; m[2] = r2; m[3] = r3;
 #pragma unroll
-    for (int i = 0; i < 16; i++) m[i] = mp[i];
+    for (int i = 4; i < 16; i++) m[i] = mp[i];
 #pragma unroll
     for (int u = 0; u < RAMPS; u++) {
         if (u & ((1 << K0) | (1 << K1))) continue;
@@ -190,114 +207,121 @@ __device__ __forceinline__ void reg_pauli(cplx (&v)[RAMPS], unsigned lyz, int ba
     }
 }
 
+// phase star on the amplitudes selected by `on` (bit u): v[u] *= eb * m[u]
+__device__ __forceinline__ void reg_star(cplx (&v)[RAMPS], cplx eb, const cplx* __restrict__ mu, unsigned on) {
+#pragma unroll
+    for (int u = 0; u < RAMPS; u++) {
+        const cplx f = cmul(eb, mu[u]);
+        v[u] = csel((on >> u) & 1, cmul(v[u], f), v[u]);
+    }
+}
+template <int L>      // centre = round bit L: only the 8 amplitudes with that bit set are touched (no selects)
+__device__ __forceinline__ void reg_star_bit(cplx (&v)[RAMPS], cplx eb, const cplx* __restrict__ mu) {
+#pragma unroll
+    for (int u = 0; u < RAMPS; u++) {
+        if (!(u & (1 << L))) continue;
+        v[u] = cmul(v[u], cmul(eb, mu[u]));
+    }
+}
+
 // ------------------------------------------------------------------------------------------
-// one register round on one tile
+// one register round on one tile.  The op loop is software-pipelined: while gate o runs on the FP64 pipe, the
+// dispatch quad and the first four matrix entries (or the phase-star table entries) of gate o+1 are already in flight,
+// so the shared-memory latency of the descriptors never sits between two gates.
+// `active` (bit i <-> op i of the pass) holds the tile-uniform tests: external controls, external star centres.
 // ------------------------------------------------------------------------------------------
 __device__ __forceinline__ void reg_round(cplx* __restrict__ t, const RoundHdr& rd, const TileOp* __restrict__ ops, qindex base,
-                                          const StarTab* __restrict__ tabs, const cplx* __restrict__ starF) {
+                                          unsigned long long active, const StarTab* __restrict__ tabs, const cplx* __restrict__ starF) {
     const int tid = threadIdx.x;
     const int b0 = rd.b[0], b1 = rd.b[1], b2 = rd.b[2], b3 = rd.b[3];          // ascending tile-bit positions
     const unsigned jb = ins0(ins0(ins0(ins0((unsigned)tid, b0), b1), b2), b3);
     const unsigned o0 = 1u << b0, o1 = 1u << b1, o2 = 1u << b2, o3 = 1u << b3;
 #define OFF(u) ((((u) & 1) ? o0 : 0u) | (((u) & 2) ? o1 : 0u) | (((u) & 4) ? o2 : 0u) | (((u) & 8) ? o3 : 0u))
+    const int first = rd.opBase, num = rd.numOps;
+    const TileOp* op = ops + first;
+    active >>= first;
+
+    // prefetch of op `q`: dispatch quad + four complex operands
+    int4 d; cplx pa, pb, pc, pd;
+#define PREFETCH(q, D, A, B, C_, D_) do { \
+        D = *reinterpret_cast<const int4*>(q); \
+        if (D.x >= CODE_STAR) { const StarTab& tb_ = tabs[(q)->tab]; A = __ldg(&tb_.in[0][jb & 63]); B = __ldg(&tb_.in[1][jb >> 6]); C_ = starF[(q) - ops]; D_ = C_; } \
+        else { A = (q)->m[0]; B = (q)->m[1]; C_ = (q)->m[2]; D_ = (q)->m[3]; } } while (0)
+    PREFETCH(op, d, pa, pb, pc, pd);
+
     cplx v[RAMPS];
 #pragma unroll
     for (int u = 0; u < RAMPS; u++) v[u] = t[jb | OFF(u)];
 
-    for (int o = 0; o < rd.numOps; o++) {
-        const TileOp& op = ops[rd.opBase + o];
-        if (((unsigned long long)base & op.extCtrlMask) != op.extCtrlVals) continue;      // tile-uniform
-        unsigned ok = 0xFFFFu;
-        const bool nc = op.inCtrlMask == 0;
-        if (!nc) {
-            ok = 0;
+    for (int o = 0; o < num; o++, op++, active >>= 1) {
+        int4 dn = d; cplx na = pa, nb = pb, nc_ = pc, nd = pd;
+        if (o + 1 < num) PREFETCH(op + 1, dn, na, nb, nc_, nd);
+        if (active & 1) {
+            unsigned ok = 0xFFFFu;
+            const unsigned cm = (unsigned)d.z, cv = (unsigned)d.w;
+            if (cm) {
+                ok = 0;
 #pragma unroll
-            for (int u = 0; u < RAMPS; u++) ok |= (unsigned)(((jb | OFF(u)) & op.inCtrlMask) == op.inCtrlVals) << u;
-        }
-        switch (op.kind) {
-        case OP_DENSE1:
-            switch (op.l0) {
-            case 0: if (nc) reg_dense1<0, false>(v, op.m, ok); else reg_dense1<0, true>(v, op.m, ok); break;
-            case 1: if (nc) reg_dense1<1, false>(v, op.m, ok); else reg_dense1<1, true>(v, op.m, ok); break;
-            case 2: if (nc) reg_dense1<2, false>(v, op.m, ok); else reg_dense1<2, true>(v, op.m, ok); break;
-            default: if (nc) reg_dense1<3, false>(v, op.m, ok); else reg_dense1<3, true>(v, op.m, ok); break;
+                for (int u = 0; u < RAMPS; u++) ok |= (unsigned)(((jb | OFF(u)) & cm) == cv) << u;
             }
-            break;
-        case OP_DENSE2:
-            switch (op.l0 * 4 + op.l1) {
-            case 1: if (nc) reg_dense2<0, 1, false>(v, op.m, ok); else reg_dense2<0, 1, true>(v, op.m, ok); break;
-            case 2: if (nc) reg_dense2<0, 2, false>(v, op.m, ok); else reg_dense2<0, 2, true>(v, op.m, ok); break;
-            case 3: if (nc) reg_dense2<0, 3, false>(v, op.m, ok); else reg_dense2<0, 3, true>(v, op.m, ok); break;
-            case 6: if (nc) reg_dense2<1, 2, false>(v, op.m, ok); else reg_dense2<1, 2, true>(v, op.m, ok); break;
-            case 7: if (nc) reg_dense2<1, 3, false>(v, op.m, ok); else reg_dense2<1, 3, true>(v, op.m, ok); break;
-            default: if (nc) reg_dense2<2, 3, false>(v, op.m, ok); else reg_dense2<2, 3, true>(v, op.m, ok); break;
-            }
-            break;
-        case OP_SWAP:
-            switch (op.l0 * 4 + op.l1) {
-            case 1: reg_swap<0, 1>(v, ok); break;
-            case 2: reg_swap<0, 2>(v, ok); break;
-            case 3: reg_swap<0, 3>(v, ok); break;
-            case 6: reg_swap<1, 2>(v, ok); break;
-            case 7: reg_swap<1, 3>(v, ok); break;
-            default: reg_swap<2, 3>(v, ok); break;
-            }
-            break;
-        case OP_PAULI: {
-            // sign bits of the Y/Z mask: those among the round's bits vary with u, the rest is fixed for this thread
-            const int basePar = (__popc(jb & op.inMaskB) + parity64((unsigned long long)base & op.extMaskB)) & 1;
-            const cplx af = op.m[0], pf = op.m[1];
-            const unsigned lyz = op.lmaskB;
-            switch (op.lmaskA) {
-#define PC(X) case X: reg_pauli<X>(v, lyz, basePar, af, pf, ok); break;
-            PC(1) PC(2) PC(3) PC(4) PC(5) PC(6) PC(7) PC(8) PC(9) PC(10) PC(11) PC(12) PC(13) PC(14)
-            default: reg_pauli<15>(v, lyz, basePar, af, pf, ok); break;
+            switch (d.x) {
+#define D1(L) case CODE_DENSE1 + 2 * L: reg_dense1<L, false>(v, pa, pb, pc, pd, ok); break; \
+              case CODE_DENSE1 + 2 * L + 1: reg_dense1<L, true>(v, pa, pb, pc, pd, ok); break;
+            D1(0) D1(1) D1(2) D1(3)
+#undef D1
+#define D2(I, A, B) case CODE_DENSE2 + 2 * I: reg_dense2<A, B, false>(v, pa, pb, pc, pd, op->m, ok); break; \
+                    case CODE_DENSE2 + 2 * I + 1: reg_dense2<A, B, true>(v, pa, pb, pc, pd, op->m, ok); break;
+            D2(0, 0, 1) D2(1, 0, 2) D2(2, 0, 3) D2(3, 1, 2) D2(4, 1, 3) D2(5, 2, 3)
+#undef D2
+            case CODE_SWAP + 0: reg_swap<0, 1>(v, ok); break;
+            case CODE_SWAP + 1: reg_swap<0, 2>(v, ok); break;
+            case CODE_SWAP + 2: reg_swap<0, 3>(v, ok); break;
+            case CODE_SWAP + 3: reg_swap<1, 2>(v, ok); break;
+            case CODE_SWAP + 4: reg_swap<1, 3>(v, ok); break;
+            case CODE_SWAP + 5: reg_swap<2, 3>(v, ok); break;
+#define PC(X) case CODE_PAULI + X - 1: reg_pauli<X>(v, op->lmaskB, (__popc(jb & op->inMaskB) + parity64((unsigned long long)base & op->extMaskB)) & 1, pa, pb, ok); break;
+            // sign bits of the Y/Z mask: those among the round's bits vary with u (lmaskB), the rest is fixed for this thread
+            PC(1) PC(2) PC(3) PC(4) PC(5) PC(6) PC(7) PC(8) PC(9) PC(10) PC(11) PC(12) PC(13) PC(14) PC(15)
 #undef PC
-            }
-        } break;
-        case OP_DIAG: {
-            const cplx m0 = op.m[0], m1 = op.m[1], m2 = op.m[2], m3 = op.m[3];
-            const int x0 = (op.p0 < 0) ? getBit(base, op.e0) : 0;
-            const int x1 = (op.numT > 1 && op.p1 < 0) ? getBit(base, op.e1) : 0;
+            case CODE_DIAG: {
+                const int p0 = op->p0, p1 = op->p1, numT = op->numT;
+                const int x0 = (p0 < 0) ? getBit(base, op->e0) : 0;
+                const int x1 = (numT > 1 && p1 < 0) ? getBit(base, op->e1) : 0;
 #pragma unroll
-            for (int u = 0; u < RAMPS; u++) {
-                const unsigned j = jb | OFF(u);
-                const int k0 = (op.p0 < 0) ? x0 : ((j >> op.p0) & 1);
-                const int k1 = (op.numT > 1) ? ((op.p1 < 0) ? x1 : ((j >> op.p1) & 1)) : 0;
-                const cplx f = k1 ? (k0 ? m3 : m2) : (k0 ? m1 : m0);
-                v[u] = csel((ok >> u) & 1, cmul(v[u], f), v[u]);
-            }
-        } break;
-        case OP_PARITY: {
-            const cplx f0 = op.m[0], f1 = op.m[1];
-            const int extPar = parity64((unsigned long long)base & op.extMaskB);
+                for (int u = 0; u < RAMPS; u++) {
+                    const unsigned j = jb | OFF(u);
+                    const int k0 = (p0 < 0) ? x0 : ((j >> p0) & 1);
+                    const int k1 = (numT > 1) ? ((p1 < 0) ? x1 : ((j >> p1) & 1)) : 0;
+                    const cplx f = k1 ? (k0 ? pd : pc) : (k0 ? pb : pa);
+                    v[u] = csel((ok >> u) & 1, cmul(v[u], f), v[u]);
+                }
+            } break;
+            case CODE_PARITY: {
+                const unsigned inA = op->inMaskA;
+                const int extPar = parity64((unsigned long long)base & op->extMaskB);
 #pragma unroll
-            for (int u = 0; u < RAMPS; u++) {
-                const unsigned j = jb | OFF(u);
-                const int par = (__popc(j & op.inMaskA) + extPar) & 1;
-                v[u] = csel((ok >> u) & 1, cmul(v[u], par ? f1 : f0), v[u]);
+                for (int u = 0; u < RAMPS; u++) {
+                    const int par = (__popc((jb | OFF(u)) & inA) + extPar) & 1;
+                    v[u] = csel((ok >> u) & 1, cmul(v[u], par ? pb : pa), v[u]);
+                }
+            } break;
+            // phase star: amplitudes with the centre bit set gain exp(i sum_c theta_c bit_c).  The phase is additive over
+            // index bits, so it factors into a per-thread part (tile bits outside the round: two 64-entry tables, times
+            // the per-tile factor of the bits outside the tile -- all three prefetched) and a per-register part op->m[u]
+            case CODE_STAR + 0: reg_star_bit<0>(v, cmul(cmul(pa, pb), pc), op->m); break;
+            case CODE_STAR + 1: reg_star_bit<1>(v, cmul(cmul(pa, pb), pc), op->m); break;
+            case CODE_STAR + 2: reg_star_bit<2>(v, cmul(cmul(pa, pb), pc), op->m); break;
+            case CODE_STAR + 3: reg_star_bit<3>(v, cmul(cmul(pa, pb), pc), op->m); break;
+            default:            // CODE_STAR + 4: centre outside the round (a tile bit tested through `ok`, or external and set)
+                if (ok) reg_star(v, cmul(cmul(pa, pb), pc), op->m, ok);
+                break;
             }
-        } break;
-        case OP_STAR: {
-            // amplitudes with centre bit 1 gain exp(i sum_c theta_c bit_c): product of per-segment table entries
-            // phase(j) is additive over the bits of j, so it splits into a per-thread factor (tile bits outside the
-            // round, via the two 64-entry tables, times the per-tile external factor) and a per-register factor
-            // op.m[u] (the round's own bits; identical for every thread, precomputed on the host)
-            const StarTab& tb = tabs[op.tab];
-            if (op.p0 < 0 && !getBit(base, op.e0)) break;
-            const cplx eb = cmul(cmul(__ldg(&tb.in[0][jb & 63]), __ldg(&tb.in[1][jb >> 6])), starF[rd.opBase + o]);
-            const bool fixedOn = (op.p0 < 0) || (op.l0 < 0 && ((jb >> op.p0) & 1));
-            if (op.l0 < 0 && !fixedOn) break;          // centre is a non-round tile bit that is 0 for this thread
-#pragma unroll
-            for (int u = 0; u < RAMPS; u++) {
-                const bool on = (op.l0 < 0) ? true : ((u >> op.l0) & 1);
-                v[u] = csel(on, cmul(v[u], cmul(eb, op.m[u])), v[u]);
-            }
-        } break;
         }
+        d = dn; pa = na; pb = nb; pc = nc_; pd = nd;
     }
 #pragma unroll
     for (int u = 0; u < RAMPS; u++) t[jb | OFF(u)] = v[u];
+#undef PREFETCH
 #undef OFF
 }
 
@@ -356,6 +380,9 @@ __global__ void __launch_bounds__(TILE_BLOCK, 1) k_tile_pass(cplx* __restrict__ 
     const int lane = tid & 31;
 
     if (tid >= TILE_THREADS) {
+        // the copy warpgroup hands most of its registers to the two compute warpgroups; only its first warp works
+        asm volatile("setmaxnreg.dec.sync.aligned.u32 %0;" :: "n"(COPY_REGS));
+        if (tid >= TILE_THREADS + 32) return;
         // ---------------- copy warp: keeps every stage either loading, being computed, or draining ----------------
         auto issue_load = [&](qindex k) {
             const int s = (int)(k % TILE_STAGES);
@@ -387,6 +414,7 @@ __global__ void __launch_bounds__(TILE_BLOCK, 1) k_tile_pass(cplx* __restrict__ 
     }
 
     // ---------------- compute warps ----------------
+    asm volatile("setmaxnreg.inc.sync.aligned.u32 %0;" :: "n"(COMPUTE_REGS));
     for (qindex k = 0; k < myCount; k++) {
         const int s = (int)(k % TILE_STAGES);
         const unsigned parity = (unsigned)((k / TILE_STAGES) & 1);
@@ -401,16 +429,27 @@ __global__ void __launch_bounds__(TILE_BLOCK, 1) k_tile_pass(cplx* __restrict__ 
             for (int sg = 0; sg < STAR_SEGS; sg++) f = cmul(f, __ldg(&tb.ext[sg][(base >> (6 * sg)) & 63]));
             starF[k & 1][tid] = f;
         }
+        // tile-uniform tests of every op, once per tile: external controls and external phase-star centres
+        unsigned long long active = 0;
+        for (int b = 0; b < numOps; b += 32) {
+            const int o = b + lane;
+            bool a = false;
+            if (o < numOps) {
+                const TileOp& op = ops[o];
+                a = ((unsigned long long)base & op.extCtrlMask) == op.extCtrlVals;
+                if (op.kind == OP_STAR && op.p0 < 0) a = a && getBit(base, op.e0);
+            }
+            active |= (unsigned long long)__ballot_sync(0xffffffffu, a) << b;
+        }
         mbar_wait(&full[s], parity);
         compute_sync();
 
         for (int r = 0; r < numRounds; r++) {
             const RoundHdr& rd = rounds[r];
             if (rd.kind == ROUND_REG) {
-                reg_round(t, rd, ops, base, tabs, starF[k & 1]);
+                reg_round(t, rd, ops, base, active, tabs, starF[k & 1]);
             } else {
-                const TileOp& op = ops[rd.opBase];
-                if (((unsigned long long)base & op.extCtrlMask) == op.extCtrlVals) smem_pauli(t, op, base);
+                if ((active >> rd.opBase) & 1) smem_pauli(t, ops[rd.opBase], base);
             }
             if (r + 1 < numRounds) compute_sync();
         }
@@ -658,8 +697,9 @@ static void emit_pass(const qb_state* q, const std::vector<QOp>& ops, const Pass
         for (int p = 0; p < T; p++) { local[p] = -1; if ((curBits >> p) & 1) { local[p] = k; r.b[k++] = p; } }
         for (int o = curBase; o < curBase + curCount; o++) {
             TileOp& t = E.ops[opStart + o];
-            if (t.kind == OP_DENSE1) t.l0 = local[t.p0];
-            else if (t.kind == OP_SWAP) { t.l0 = std::min(local[t.p0], local[t.p1]); t.l1 = std::max(local[t.p0], local[t.p1]); }
+            const int hasCtrl = t.inCtrlMask != 0;
+            if (t.kind == OP_DENSE1) { t.l0 = local[t.p0]; t.code = CODE_DENSE1 + 2 * t.l0 + hasCtrl; }
+            else if (t.kind == OP_SWAP) { t.l0 = std::min(local[t.p0], local[t.p1]); t.l1 = std::max(local[t.p0], local[t.p1]); t.code = CODE_SWAP + pair_index(t.l0, t.l1); }
             else if (t.kind == OP_DENSE2) {
                 int a = local[t.p0], b = local[t.p1];
                 if (a > b) {        // re-order the matrix so that its index bit 0 belongs to the lower register bit
@@ -671,7 +711,7 @@ static void emit_pass(const qb_state* q, const std::vector<QOp>& ops, const Pass
                     for (int i = 0; i < 16; i++) t.m[i] = m2[i];
                     std::swap(a, b);
                 }
-                t.l0 = a; t.l1 = b;
+                t.l0 = a; t.l1 = b; t.code = CODE_DENSE2 + 2 * pair_index(a, b) + hasCtrl;
             } else if (t.kind == OP_STAR) {
                 // per-register phase factors over the round's own bits; the tables keep every other bit
                 const QOp& qo = ops[order[o]];
@@ -683,6 +723,10 @@ static void emit_pass(const qb_state* q, const std::vector<QOp>& ops, const Pass
                         for (int u = 0; u < RAMPS; u++) if ((u >> local[p]) & 1) ang[u] += ce.second;
                 }
                 for (int u = 0; u < RAMPS; u++) t.m[u] = mk((double)cosl(ang[u]), (double)sinl(ang[u]));
+                // centre among the round's bits: specialised body; centre elsewhere in the tile: a per-thread test
+                // carried by the in-tile control fields; centre outside the tile: the per-tile `active` test
+                if (t.l0 >= 0) t.code = CODE_STAR + t.l0;
+                else { t.code = CODE_STAR + 4; if (t.p0 >= 0) { t.inCtrlMask = 1u << t.p0; t.inCtrlVals = 1u << t.p0; } }
             } else if (t.kind == OP_PAULI) {
                 t.lmaskA = t.lmaskB = 0;
                 for (int p = 0; p < T; p++) if (local[p] >= 0) {
@@ -690,7 +734,9 @@ static void emit_pass(const qb_state* q, const std::vector<QOp>& ops, const Pass
                     if ((t.inMaskB >> p) & 1) t.lmaskB |= 1u << local[p];
                 }
                 t.inMaskB &= ~curBits;          // the kernel adds the round bits' parity through lmaskB
-            }
+                t.code = CODE_PAULI + (int)t.lmaskA - 1;
+            } else if (t.kind == OP_DIAG) t.code = CODE_DIAG;
+            else if (t.kind == OP_PARITY) t.code = CODE_PARITY;
         }
         E.rounds.push_back(r);
         curBits = 0; curCount = 0;

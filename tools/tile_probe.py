@@ -15,7 +15,11 @@ u4c = capi.cplx_array(u4)
 E = capi.ints([])
 lib = capi.lib()
 
+ONLY = os.environ.get("PROBE_ONLY", "")
+
 def run(label, gates, reps=5):
+    if ONLY and not any(k in label for k in ONLY.split("|")):
+        return
     def issue():
         for g in gates:
             if g[0] == "h": lib.qb_statevec_anyCtrlOneTargDenseMatr_subA(ref, E, E, 0, g[1], h)
