@@ -17,8 +17,9 @@
 // among the 4 bits (diagonal gates always qualify) and writes the 16 amplitudes back: one shared-memory round trip
 // and one barrier per ROUND instead of per gate.
 //
-// KERNEL.  One persistent CTA per SM (grid = #SMs): 8 compute warps (256 threads x 16 amplitudes, 232 registers each
-// after setmaxnreg) + 1 copy warp (its warpgroup gives its registers away),
+// KERNEL.  One persistent CTA per SM (grid = #SMs): two compute warpgroups (128 threads each, 232 registers per thread
+// after setmaxnreg; each owns one tile at a time and walks it in two 16-amplitude register blocks per thread and round)
+// + 1 copy warp (its warpgroup gives its registers away),
 // 3 stages x 64 KiB of shared memory.  The copy warp drives the copy engine: cp.async.bulk (TMA, 1-D) loads the chunks
 // of a tile into a free stage, signalling the stage's `full` mbarrier with complete_tx; the compute warps wait on it,
 // run the pass's rounds on the tile, fence.proxy.async and arrive on the stage's `done` mbarrier; the copy warp then
@@ -39,12 +40,14 @@
 #define TILE_LOW 6
 #define TILE_AMPS (1 << TILE_BITS)
 #define TILE_STAGES 3
-#define TILE_THREADS 256              // compute threads (8 warps); one more warp (the last) only drives the copy engine
+#define TILE_THREADS 256              // compute threads: two independent warpgroups of WG_THREADS, each working on its own tile
+#define WG_THREADS 128
+#define WG_ITERS (TILE_AMPS / (WG_THREADS * RAMPS))   // register blocks per thread and round (2)
 #define TILE_BLOCK (TILE_THREADS + 128)  // + one warpgroup whose first warp is the copy warp (register re-allocation is per warpgroup)
 #define COMPUTE_REGS 232              // setmaxnreg: 384 x 168 at launch -> 256 x 232 (compute) + 128 x 40 (copy warpgroup)
 #define COPY_REGS 40
 #define RB 4                          // tile bits held in registers per round
-#define RAMPS (1 << RB)               // amplitudes per thread: TILE_THREADS * RAMPS == TILE_AMPS
+#define RAMPS (1 << RB)               // amplitudes per register block
 #define TILE_MAX_CHUNKS (1 << (TILE_BITS - TILE_LOW))
 #define MAX_OPS_PER_PASS 48
 #define QUEUE_MAX 512
@@ -231,8 +234,10 @@ __device__ __forceinline__ void reg_star_bit(cplx (&v)[RAMPS], cplx eb, const cp
 // `active` (bit i <-> op i of the pass) holds the tile-uniform tests: external controls, external star centres.
 // ------------------------------------------------------------------------------------------
 __device__ __forceinline__ void reg_round(cplx* __restrict__ t, const RoundHdr& rd, const TileOp* __restrict__ ops, qindex base,
-                                          unsigned long long active, const StarTab* __restrict__ tabs, const cplx* __restrict__ starF) {
-    const int tid = threadIdx.x;
+                                          unsigned long long active0, const StarTab* __restrict__ tabs, const cplx* __restrict__ starF, int wtid) {
+  for (int it = 0; it < WG_ITERS; it++) {
+    const int tid = wtid + it * WG_THREADS;
+    unsigned long long active = active0;
     const int b0 = rd.b[0], b1 = rd.b[1], b2 = rd.b[2], b3 = rd.b[3];          // ascending tile-bit positions
     const unsigned jb = ins0(ins0(ins0(ins0((unsigned)tid, b0), b1), b2), b3);
     const unsigned o0 = 1u << b0, o1 = 1u << b1, o2 = 1u << b2, o3 = 1u << b3;
@@ -321,19 +326,20 @@ __device__ __forceinline__ void reg_round(cplx* __restrict__ t, const RoundHdr& 
     }
 #pragma unroll
     for (int u = 0; u < RAMPS; u++) t[jb | OFF(u)] = v[u];
+  }
 #undef PREFETCH
 #undef OFF
 }
 
 // shared-memory fallback for the one gate shape that cannot live in a 4-bit register round:
 // Pauli strings with X/Y on more than four tile bits
-__device__ __forceinline__ void smem_pauli(cplx* __restrict__ t, const TileOp& op, qindex base) {
+__device__ __forceinline__ void smem_pauli(cplx* __restrict__ t, const TileOp& op, qindex base, int wtid) {
     const unsigned cm = op.inCtrlMask, cv = op.inCtrlVals;
     const unsigned xy = op.inMaskA, yz = op.inMaskB;
     const int h = 31 - __clz(xy);
     const int extPar = parity64((unsigned long long)base & op.extMaskB);
     const cplx af = op.m[0], pf = op.m[1];
-    for (unsigned n = threadIdx.x; n < TILE_AMPS / 2; n += TILE_THREADS) {
+    for (unsigned n = wtid; n < TILE_AMPS / 2; n += WG_THREADS) {
         unsigned jA = ins0(n, h);
         if ((jA & cm) != cv) continue;
         unsigned jB = jA ^ xy;
@@ -348,7 +354,7 @@ __device__ __forceinline__ void smem_pauli(cplx* __restrict__ t, const TileOp& o
 __device__ __forceinline__ void mbar_arrive(unsigned long long* bar) {
     asm volatile("mbarrier.arrive.shared::cta.b64 _, [%0];" :: "r"(smem_u32(bar)) : "memory");
 }
-__device__ __forceinline__ void compute_sync() { asm volatile("bar.sync 1, %0;" :: "n"(TILE_THREADS) : "memory"); }
+__device__ __forceinline__ void wg_sync(int wg) { asm volatile("bar.sync %0, %1;" :: "r"(1 + wg), "n"(WG_THREADS) : "memory"); }
 
 __global__ void __launch_bounds__(TILE_BLOCK, 1) k_tile_pass(cplx* __restrict__ amps, const PassHdr* __restrict__ hdrp,
         const RoundHdr* __restrict__ grounds, const TileOp* __restrict__ gops, const StarTab* __restrict__ tabs) {
@@ -359,7 +365,7 @@ __global__ void __launch_bounds__(TILE_BLOCK, 1) k_tile_pass(cplx* __restrict__ 
     __shared__ unsigned long long done[TILE_STAGES];     // compute warps -> copy warp: the tile is computed
     __shared__ PassHdr hdr;
     __shared__ RoundHdr rounds[MAX_OPS_PER_PASS];
-    __shared__ cplx starF[2][MAX_OPS_PER_PASS];  // double-buffered: a fast warp may start tile k+1 while a slow one finishes tile k
+    __shared__ cplx starF[2][2][MAX_OPS_PER_PASS];  // per warpgroup, double-buffered: a fast warp may start its next tile while a slow one finishes
 
     const int tid = threadIdx.x;
     for (int i = tid; i < (int)(sizeof(PassHdr) / 4); i += TILE_BLOCK) ((int*)&hdr)[i] = ((const int*)hdrp)[i];
@@ -368,7 +374,7 @@ __global__ void __launch_bounds__(TILE_BLOCK, 1) k_tile_pass(cplx* __restrict__ 
     for (int i = tid; i < numOps * (int)(sizeof(TileOp) / 4); i += TILE_BLOCK) ((int*)ops)[i] = ((const int*)gops)[i];
     for (int i = tid; i < numRounds * (int)(sizeof(RoundHdr) / 4); i += TILE_BLOCK) ((int*)rounds)[i] = ((const int*)grounds)[i];
     if (tid == 0) {
-        for (int s = 0; s < TILE_STAGES; s++) { mbar_init(&full[s], 1); mbar_init(&done[s], TILE_THREADS / 32); }
+        for (int s = 0; s < TILE_STAGES; s++) { mbar_init(&full[s], 1); mbar_init(&done[s], WG_THREADS / 32); }
         asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
     }
     __syncthreads();
@@ -415,19 +421,23 @@ __global__ void __launch_bounds__(TILE_BLOCK, 1) k_tile_pass(cplx* __restrict__ 
 
     // ---------------- compute warps ----------------
     asm volatile("setmaxnreg.inc.sync.aligned.u32 %0;" :: "n"(COMPUTE_REGS));
-    for (qindex k = 0; k < myCount; k++) {
+    // two warpgroups, each taking every other tile of this CTA and running it alone (own named barrier): their phases
+    // drift apart, so one group's shared-memory traffic, barriers and gate dispatch overlap the other's FP64 work
+    const int wg = tid / WG_THREADS, wtid = tid % WG_THREADS;
+    for (qindex k = wg; k < myCount; k += 2) {
         const int s = (int)(k % TILE_STAGES);
         const unsigned parity = (unsigned)((k / TILE_STAGES) & 1);
         const qindex base = hdr.tileIns((qindex)blockIdx.x + k * gridDim.x);
         cplx* t = stageBuf + (size_t)s * TILE_AMPS;
+        cplx* sf = starF[wg][(k >> 1) & 1];
 
         // per-tile factor of every phase star: the part of its phase that depends on bits OUTSIDE the tile
-        if (tid < numOps && ops[tid].kind == OP_STAR) {
-            const StarTab& tb = tabs[ops[tid].tab];
+        if (wtid < numOps && ops[wtid].kind == OP_STAR) {
+            const StarTab& tb = tabs[ops[wtid].tab];
             cplx f = mk(1, 0);
 #pragma unroll
             for (int sg = 0; sg < STAR_SEGS; sg++) f = cmul(f, __ldg(&tb.ext[sg][(base >> (6 * sg)) & 63]));
-            starF[k & 1][tid] = f;
+            sf[wtid] = f;
         }
         // tile-uniform tests of every op, once per tile: external controls and external phase-star centres
         unsigned long long active = 0;
@@ -442,16 +452,16 @@ __global__ void __launch_bounds__(TILE_BLOCK, 1) k_tile_pass(cplx* __restrict__ 
             active |= (unsigned long long)__ballot_sync(0xffffffffu, a) << b;
         }
         mbar_wait(&full[s], parity);
-        compute_sync();
+        wg_sync(wg);
 
         for (int r = 0; r < numRounds; r++) {
             const RoundHdr& rd = rounds[r];
             if (rd.kind == ROUND_REG) {
-                reg_round(t, rd, ops, base, active, tabs, starF[k & 1]);
+                reg_round(t, rd, ops, base, active, tabs, sf, wtid);
             } else {
-                if ((active >> rd.opBase) & 1) smem_pauli(t, ops[rd.opBase], base);
+                if ((active >> rd.opBase) & 1) smem_pauli(t, ops[rd.opBase], base, wtid);
             }
-            if (r + 1 < numRounds) compute_sync();
+            if (r + 1 < numRounds) wg_sync(wg);
         }
         // hand the tile to the copy warp: make this warp's shared-memory writes visible to the async proxy, then arrive
         fence_async_smem();
