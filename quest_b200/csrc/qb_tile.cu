@@ -451,6 +451,11 @@ __global__ void __launch_bounds__(TILE_BLOCK, 1) k_tile_pass(cplx* __restrict__ 
             }
             active |= (unsigned long long)__ballot_sync(0xffffffffu, a) << b;
         }
+        // The stage's previous tile (k - 3) belonged to the OTHER warpgroup.  A parity wait only tells the current phase
+        // from the preceding one, so this group must not poll `full` for tile k while the barrier may still be in the
+        // phase of tile k - 3: first see that tile consumed (its `done` phase is unambiguous here -- the phase before it
+        // was completed by this very group), after which `full` can only be in tile k's phase or past it.
+        if (k >= TILE_STAGES) mbar_wait(&done[s], (unsigned)(((k - TILE_STAGES) / TILE_STAGES) & 1));
         mbar_wait(&full[s], parity);
         wg_sync(wg);
 

@@ -58,3 +58,8 @@ capi.call("qb_set_tile_engine", 0)
 run("direct: 1xH q29", [("h", 29)])
 run("direct: 1xH q0", [("h", 0)])
 run("direct: 1x m2 (24,25)", [("m2", 24, 25)])
+capi.call("qb_set_tile_engine", 2)
+run("dbg: H8,H9 (contiguous tile)", [("h", 8), ("h", 9)])
+run("dbg: H6,H7 (contiguous tile)", [("h", 6), ("h", 7)])
+run("dbg: H0,H1 (contiguous tile)", [("h", 0), ("h", 1)])
+run("dbg: H12,H13", [("h", 12), ("h", 13)])
