@@ -4,8 +4,9 @@ the sharding logic (quest_b200/shim/localiser_b200.cpp), the NCCL control plane 
 kernels are all on the measured path.
 
 Timing: CUDA events on the library's stream (the legacy default stream, which is also torch's current
-stream), bracketed by barrier + synchronize, max over ranks.  `value` counts gates of the whole job per
-second: every rank applies every gate to its shard, so the job's gate count is the circuit's gate count.
+stream), bracketed by barrier + synchronize, max over ranks.  The metric's unit is one gate applied to 2^30
+amplitudes (BASELINE.json: "30q fp64 gates/s"): every rank applies every gate of the circuit to its 2^30-amplitude
+shard, so the job processes world x num_gates such units per step and `value` = world * num_gates / step time.
 """
 import json
 import math
@@ -87,6 +88,7 @@ def run(args, rank, world, local_rank, n, n_local, config, dist):
     e0.record()
     for _ in range(args.steps):
         gates()
+    Q.syncQuESTEnv()                   # restores the canonical qubit order (lazy relabelling) inside the timed region
     e1.record()
     barrier()
     clocks = sampler.stop() if rank == 0 else None
@@ -152,9 +154,11 @@ def run(args, rank, world, local_rank, n, n_local, config, dist):
         local = classes.get("local", {"hbm_algorithmic_gbs": 0.0, "hbm_algorithmic_bytes": 0, "gates": 1})
         link_bytes = sum(c["link_bytes_per_dir"] for c in classes.values())
         link_ms = sum(c["ms"] for k, c in classes.items() if k != "local")
-        config.update({"parallelism": f"state sharded over {world} GPUs on the top {int(math.log2(world))} qubits",
+        config.update({"unit_definition": "one gate applied to one 2^30-amplitude shard; a gate of the sharded circuit counts once per GPU",
+                       "circuit_gates_per_s": num_gates / (ms_per_step * 1e-3),
+                       "parallelism": f"state sharded over {world} GPUs on the top {int(math.log2(world))} qubits",
                        "p2p_nvlink_kernels": bool(p2p), "total_prob_after_run": total_prob, "gate_classes": classes})
-        line = {"metric": "30q-per-GPU fp64 gates/s (weak scaling)", "value": num_gates / (ms_per_step * 1e-3), "unit": "gates/s",
+        line = {"metric": "30q-per-GPU fp64 gates/s (weak scaling)", "value": world * num_gates / (ms_per_step * 1e-3), "unit": "gates/s",
                 "n_gpus": world, "steps": args.steps, "warmup": args.warmup, "ms_per_step": ms_per_step, "higher_is_better": True,
                 "scaling": "weak", "vs_baseline": None, "dtype": "f64", "data": "synthetic", "config": config,
                 "roofline": {"kernel": "local gate kernels (per GPU)", "bound": "hbm", "achieved": local["hbm_algorithmic_gbs"], "peak": peak_gbs,
@@ -164,7 +168,7 @@ def run(args, rank, world, local_rank, n, n_local, config, dist):
                                         "peak_gbs_per_dir": 770.0, "peak_source": "B200_PROFILING.md measured peer copy (900 nominal)",
                                         "non_local_gates": sum(c["gates"] for k, c in classes.items() if k != "local")}},
                 "cpu_baseline": None,
-                "e2e": {"value": num_gates / e2e_s, "unit": "gates/s", "h2d_bytes_per_step": sum(64 if op[0] == "m1" else 256 for op in dense),
+                "e2e": {"value": world * num_gates / e2e_s, "unit": "gates/s", "h2d_bytes_per_step": sum(64 if op[0] == "m1" else 256 for op in dense),
                         "d2h_bytes_per_step": 8, "ms_per_step": 1e3 * e2e_s, "result_prob_of_top_qubit_0": prob},
                 "gpu_launches": int(launches), "clocks": clocks}
         print(json.dumps(line))

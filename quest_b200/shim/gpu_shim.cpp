@@ -32,6 +32,7 @@
 #include "quest/src/gpu/gpu_subroutines.hpp"
 
 #include "quest_b200.h"
+#include "qubit_map.hpp"
 
 #include <array>
 #include <set>
@@ -165,7 +166,7 @@ bool gpu_areAnyNodesBoundToSameGpu() {
     return ! globalGpusAreUnique;
 }
 
-void gpu_sync() { QB_CHECK( qb_sync() ); }
+void gpu_sync() { qbmap_canonicaliseAll(); QB_CHECK( qb_sync() ); }     // syncQuESTEnv(): restore canonical qubit order first
 
 void gpu_initCuQuantum()     { error_cuQuantumInitOrFinalizedButNotCompiled(); }
 void gpu_finalizeCuQuantum() { error_cuQuantumInitOrFinalizedButNotCompiled(); }
@@ -182,12 +183,12 @@ qcomp* gpu_allocArray(qindex length) {
     return reinterpret_cast<qcomp*>(ptr);   // nullptr on out-of-memory, handled by validation
 }
 
-void gpu_deallocArray(qcomp* amps) { QB_CHECK( qb_free(qp(amps)) ); }
+void gpu_deallocArray(qcomp* amps) { qbmap_forget(amps); QB_CHECK( qb_free(qp(amps)) ); }
 
 void gpu_copyArray(qcomp* dest, qcomp* src, qindex dim) { QB_CHECK( qb_copy_d2d(qp(dest), qp(src), dim) ); }
 
-void gpu_copyCpuToGpu(qcomp* cpuArr, qcomp* gpuArr, qindex numElems) { QB_CHECK( qb_copy_h2d(qp(gpuArr), qp(cpuArr), numElems) ); }
-void gpu_copyGpuToCpu(qcomp* gpuArr, qcomp* cpuArr, qindex numElems) { QB_CHECK( qb_copy_d2h(qp(cpuArr), qp(gpuArr), numElems) ); }
+void gpu_copyCpuToGpu(qcomp* cpuArr, qcomp* gpuArr, qindex numElems) { qbmap_canonicaliseHolding(gpuArr); QB_CHECK( qb_copy_h2d(qp(gpuArr), qp(cpuArr), numElems) ); }
+void gpu_copyGpuToCpu(qcomp* gpuArr, qcomp* cpuArr, qindex numElems) { qbmap_canonicaliseHolding(gpuArr); QB_CHECK( qb_copy_d2h(qp(cpuArr), qp(gpuArr), numElems) ); }
 
 void gpu_copyCpuToGpu(Qureg qureg, qcomp* cpuArr, qcomp* gpuArr, qindex numElems) {
     assert_quregIsGpuAccelerated(qureg);

@@ -40,11 +40,14 @@
 #include "quest/src/gpu/gpu_config.hpp"
 
 #include "quest_b200.h"
+#include "qubit_map.hpp"
 
 #include <algorithm>
 #include <array>
 #include <complex>
+#include <cstdlib>
 #include <map>
+#include <unordered_map>
 #include <tuple>
 #include <vector>
 
@@ -53,6 +56,7 @@ using std::tuple;
 
 // defined in api/paulis.cpp and api/qureg.cpp (unchanged reference host code)
 extern bool paulis_containsXOrY(PauliStr str);
+extern int paulis_getPauliAt(PauliStr str, int ind);
 extern vector<int> paulis_getInds(PauliStr str);
 extern std::array<vector<int>,3> paulis_getSeparateInds(PauliStr str, Qureg qureg);
 extern int paulis_getPrefixZSign(Qureg qureg, vector<int> prefixZ);
@@ -133,6 +137,182 @@ static qb_state toState(Qureg q) {
     s.logNumColsPerNode = (int) q.logNumColsPerNode;
     s.isDensityMatrix = q.isDensityMatrix;
     return s;
+}
+
+
+/*
+ * LAZY QUBIT RELABELLING
+ *
+ * Per GPU statevector (keyed by the device pointer; Quregs are passed by value) a permutation logical qubit ->
+ * index bit is kept on every rank (all ranks issue the same API calls, so the copies agree).  It starts as the
+ * identity and changes in two ways:
+ *   - an uncontrolled SWAP only exchanges two entries (no amplitude moves);
+ *   - a dense gate whose target currently sits on a rank bit ("prefix") pulls it into the shard with ONE
+ *     half-shard exchange against the least-recently-used high suffix qubit and leaves it there, where the
+ *     reference swaps in, applies, and swaps back (localiser.cpp:997-1040) -- half the link traffic, and the
+ *     next gates on that qubit are local.
+ * Relabelling-aware entry points translate their qubit arguments; every other entry point first restores the
+ * identity (qbmap_canon), so the permutation is never observable through QuEST's API.
+ */
+
+struct QubitMap {
+    Qureg qureg;                              // by-value copy (pointers + dimensions): enough to issue swaps later
+    std::vector<int> phys;                    // phys[logical] = index bit holding that qubit
+    std::vector<int> logi;                    // logi[index bit] = logical qubit stored there
+    std::vector<unsigned long long> lastUse;  // per logical qubit, for the swap-in victim choice
+    unsigned long long clock = 0;
+};
+
+static std::unordered_map<const void*, QubitMap> g_qubitMaps;
+static bool g_inCanonicalise = false;
+
+static bool relabelEnabled() {
+    static int on = -1;
+    if (on < 0) { const char* e = std::getenv("QUEST_B200_RELABEL"); on = (e && e[0] == '0') ? 0 : 1; }
+    return on == 1;
+}
+
+static bool mapEligible(Qureg q) {
+    return relabelEnabled() && q.isGpuAccelerated && !q.isDensityMatrix && q.gpuAmps != nullptr && q.numQubits <= 62;
+}
+
+static QubitMap* findMap(Qureg q) {
+    if (g_qubitMaps.empty() || !mapEligible(q)) return nullptr;
+    auto it = g_qubitMaps.find(q.gpuAmps);
+    return it == g_qubitMaps.end() ? nullptr : &it->second;
+}
+
+static QubitMap& getMap(Qureg q) {
+    auto it = g_qubitMaps.find(q.gpuAmps);
+    if (it != g_qubitMaps.end()) return it->second;
+    QubitMap m;
+    m.qureg = q;
+    m.phys.resize(q.numQubits); m.logi.resize(q.numQubits); m.lastUse.assign(q.numQubits, 0);
+    for (int i = 0; i < q.numQubits; i++) m.phys[i] = m.logi[i] = i;
+    return g_qubitMaps.emplace(q.gpuAmps, std::move(m)).first->second;
+}
+
+static void relabelSwap(QubitMap& m, int logicalA, int logicalB) {
+    int pa = m.phys[logicalA], pb = m.phys[logicalB];
+    m.phys[logicalA] = pb; m.phys[logicalB] = pa;
+    m.logi[pa] = logicalB; m.logi[pb] = logicalA;
+}
+
+static void touch(QubitMap& m, int logical) { m.lastUse[logical] = ++m.clock; }
+
+static void mapQubits(QubitMap* m, vector<int>& qubits) {
+    if (!m) return;
+    for (int& q : qubits) { touch(*m, q); q = m->phys[q]; }
+}
+
+static int mapQubit(QubitMap* m, int qubit) {
+    if (!m) return qubit;
+    touch(*m, qubit);
+    return m->phys[qubit];
+}
+
+static void phys_statevec_anyCtrlSwap(Qureg qureg, vector<int> ctrls, vector<int> ctrlStates, int targ1, int targ2);
+
+// moves amplitudes so that index bits a and b trade contents, and records it
+static void physicalSwap(QubitMap& m, int a, int b) {
+    if (a == b) return;
+    phys_statevec_anyCtrlSwap(m.qureg, {}, {}, std::min(a, b), std::max(a, b));
+    int la = m.logi[a], lb = m.logi[b];
+    m.logi[a] = lb; m.logi[b] = la;
+    m.phys[la] = b; m.phys[lb] = a;
+}
+
+static void canonicalise(QubitMap& m) {
+    if (g_inCanonicalise) return;
+    g_inCanonicalise = true;
+    for (int l = 0; l < (int) m.phys.size(); l++)
+        if (m.phys[l] != l)
+            physicalSwap(m, m.phys[l], l);
+    g_inCanonicalise = false;
+}
+
+static void qbmap_canon(Qureg q) {
+    if (QubitMap* m = findMap(q)) {
+        canonicalise(*m);
+        g_qubitMaps.erase(q.gpuAmps);
+    }
+}
+
+static void qbmap_reset(Qureg q) {
+    if (!g_qubitMaps.empty() && q.gpuAmps != nullptr) g_qubitMaps.erase(q.gpuAmps);
+}
+
+void qbmap_forget(const void* gpuAmps) {
+    if (!g_qubitMaps.empty()) g_qubitMaps.erase(gpuAmps);
+}
+
+void qbmap_canonicaliseHolding(const void* gpuPtr) {
+    for (auto it = g_qubitMaps.begin(); it != g_qubitMaps.end(); ++it) {
+        const char* lo = reinterpret_cast<const char*>(it->second.qureg.gpuAmps);
+        const char* hi = lo + it->second.qureg.numAmpsPerNode * sizeof(qcomp);
+        const char* p = reinterpret_cast<const char*>(gpuPtr);
+        if (p >= lo && p < hi) { canonicalise(it->second); g_qubitMaps.erase(it); return; }
+    }
+}
+
+void qbmap_canonicaliseAll() {
+    if (g_inCanonicalise) return;
+    for (auto& kv : g_qubitMaps) canonicalise(kv.second);
+    g_qubitMaps.clear();
+}
+
+static void swapPrefixWithSuffix(Qureg qureg, vector<int> ctrls, vector<int> ctrlStates, int suffixTarg, int prefixTarg);
+
+// makes every (already translated) target an index bit of the shard: each target on a rank bit trades places with
+// the least-recently-used suffix qubit that the gate does not touch -- among the HIGH suffix bits when the shard
+// is large, so that the half-shard crossing NVLink is made of long contiguous runs.  Returns false if the gate
+// leaves no suffix qubit free (the caller then uses the swap-in-and-back path).
+static bool pullTargetsIntoShard(Qureg qureg, QubitMap& m, vector<int>& targs, const vector<int>& ctrls) {
+    const int nl = (int) qureg.logNumAmpsPerNode;
+    for (size_t i = 0; i < targs.size(); i++) {
+        if (targs[i] < nl) continue;
+        qindex used = getBitMask(targs.data(), targs.size()) | getBitMask(const_cast<int*>(ctrls.data()), ctrls.size());
+        int victim = -1;
+        for (int lo : {nl > 20 ? 16 : 0, 0}) {
+            for (int p = nl - 1; p >= lo; p--)
+                if (!getBit(used, p) && (victim < 0 || m.lastUse[m.logi[p]] < m.lastUse[m.logi[victim]]))
+                    victim = p;
+            if (victim >= 0) break;
+        }
+        if (victim < 0) return false;
+        swapPrefixWithSuffix(qureg, {}, {}, victim, targs[i]);
+        int lt = m.logi[targs[i]], lv = m.logi[victim];
+        m.logi[targs[i]] = lv; m.logi[victim] = lt;
+        m.phys[lt] = victim; m.phys[lv] = targs[i];
+        targs[i] = victim;
+    }
+    return true;
+}
+
+// translation + swap-in for a gate with non-diagonal targets; creates the map the first time a distributed
+// statevector sees a target on a rank bit
+static void relabelForDenseGate(Qureg qureg, vector<int>& ctrls, vector<int>& targs) {
+    QubitMap* m = findMap(qureg);
+    if (!m) {
+        if (!mapEligible(qureg) || !qureg.isDistributed) return;
+        bool prefixTarg = false;
+        for (int t : targs) prefixTarg |= (t >= qureg.logNumAmpsPerNode);
+        if (!prefixTarg) return;
+        m = &getMap(qureg);
+    }
+    mapQubits(m, ctrls);
+    mapQubits(m, targs);
+    if (qureg.isDistributed) pullTargetsIntoShard(qureg, *m, targs, ctrls);
+}
+
+static PauliStr mapPauliStr(QubitMap* m, PauliStr str) {
+    if (!m) return str;
+    vector<int> codes, inds;
+    for (int q = 0; q < (int) m->phys.size(); q++) {
+        int p = paulis_getPauliAt(str, q);
+        if (p != 0) { codes.push_back(p); inds.push_back(m->phys[q]); touch(*m, q); }
+    }
+    return getPauliStr(codes.data(), inds.data(), (int) codes.size());
 }
 
 
@@ -229,6 +409,7 @@ static void exchangeWhere(Qureg qureg, int pairRank, vector<int> qubits, vector<
  */
 
 qcomp localiser_statevec_getAmp(Qureg qureg, qindex globalInd) {
+    qbmap_canon(qureg);
     if (!qureg.isDistributed) {
         qcomp amp;
         accel_statevec_getAmps_sub(&amp, qureg, globalInd, 1);
@@ -243,6 +424,7 @@ qcomp localiser_statevec_getAmp(Qureg qureg, qindex globalInd) {
 }
 
 void localiser_statevec_getAmps(qcomp* outAmps, Qureg qureg, qindex globalStartInd, qindex globalNumAmps) {
+    qbmap_canon(qureg);
     if (!qureg.isDistributed) {
         accel_statevec_getAmps_sub(outAmps, qureg, globalStartInd, globalNumAmps);
         return;
@@ -266,6 +448,7 @@ void localiser_statevec_getAmps(qcomp* outAmps, Qureg qureg, qindex globalStartI
 }
 
 void localiser_densmatr_getAmps(qcomp** outAmps, Qureg qureg, qindex startRow, qindex startCol, qindex numRows, qindex numCols) {
+    qbmap_canon(qureg);
     assert_localiserGivenDensMatr(qureg);
     vector<vector<qcomp>> tempOut;                          // transposed: one contiguous column per row of temp
     util_tryAllocMatrix(tempOut, numCols, numRows, error_localiserFailedToAllocTempMemory);
@@ -286,6 +469,7 @@ void localiser_fullstatediagmatr_getElems(qcomp* outElems, FullStateDiagMatr mat
  */
 
 void localiser_statevec_setAmps(qcomp* inAmps, Qureg qureg, qindex globalStartInd, qindex globalNumAmps) {
+    qbmap_canon(qureg);
     if (!qureg.isDistributed) {
         accel_statevec_setAmps_sub(inAmps, qureg, globalStartInd, globalNumAmps);
         return;
@@ -297,6 +481,7 @@ void localiser_statevec_setAmps(qcomp* inAmps, Qureg qureg, qindex globalStartIn
 }
 
 void localiser_densmatr_setAmps(qcomp** inAmps, Qureg qureg, qindex startRow, qindex startCol, qindex numRows, qindex numCols) {
+    qbmap_canon(qureg);
     assert_localiserGivenDensMatr(qureg);
     vector<vector<qcomp>> tempAmps;
     util_tryAllocMatrix(tempAmps, numCols, numRows, error_localiserFailedToAllocTempMemory);
@@ -308,6 +493,7 @@ void localiser_densmatr_setAmps(qcomp** inAmps, Qureg qureg, qindex startRow, qi
 }
 
 void localiser_densmatr_setAmpsToPauliStrSum(Qureg qureg, PauliStrSum sum) {
+    qbmap_canon(qureg);
     assert_localiserGivenDensMatr(qureg);
     accel_densmatr_setAmpsToPauliStrSum_sub(qureg, sum);
 }
@@ -333,11 +519,13 @@ void localiser_fullstatediagmatr_setElemsToPauliStrSum(FullStateDiagMatr out, Pa
 static void mixDensityMatrixWithStatevector(qreal outProb, Qureg out, qreal inProb, Qureg in);
 
 void localiser_statevec_initArbitraryPureState(Qureg qureg, qcomp* amps) {
+    qbmap_reset(qureg);
     assert_localiserGivenStateVec(qureg);
     localiser_statevec_setAmps(amps, qureg, 0, qureg.numAmps);
 }
 
 void localiser_densmatr_initArbitraryPureState(Qureg qureg, qcomp* amps) {
+    qbmap_canon(qureg);
     assert_localiserGivenDensMatr(qureg);
     // |amps><amps| from a serial host-only view of the user's array
     Qureg spoof = qureg_populateNonHeapFields(qureg.numQubits, 0, 0, 0, 0);
@@ -346,36 +534,43 @@ void localiser_densmatr_initArbitraryPureState(Qureg qureg, qcomp* amps) {
 }
 
 void localiser_densmatr_initArbitraryMixedState(Qureg qureg, qcomp** amps) {
+    qbmap_canon(qureg);
     qindex dim = powerOf2(qureg.numQubits);
     localiser_densmatr_setAmps(amps, qureg, 0, 0, dim, dim);
 }
 
 void localiser_statevec_initUniformState(Qureg qureg, qcomp amp) {
+    qbmap_reset(qureg);
     accel_statevec_initUniformState_sub(qureg, amp);
 }
 
 void localiser_statevec_initDebugState(Qureg qureg) {
+    qbmap_reset(qureg);
     accel_statevec_initDebugState_sub(qureg);
 }
 
 void localiser_statevec_initClassicalState(Qureg qureg, qindex globalInd) {
+    qbmap_reset(qureg);
     accel_statevec_initUniformState_sub(qureg, 0);
     qcomp amp = 1;
     localiser_statevec_setAmps(&amp, qureg, globalInd, 1);
 }
 
 void localiser_densmatr_initPureState(Qureg qureg, Qureg pure) {
+    qbmap_canon(qureg); qbmap_canon(pure);
     assert_localiserGivenDensMatr(qureg);
     assert_localiserGivenStateVec(pure);
     mixDensityMatrixWithStatevector(0, qureg, 1, pure);
 }
 
 void localiser_statevec_initUnnormalisedUniformlyRandomPureStateAmps(Qureg qureg) {
+    qbmap_reset(qureg);
     assert_localiserGivenStateVec(qureg);
     accel_statevec_initUnnormalisedUniformlyRandomPureStateAmps_sub(qureg);
 }
 
 void localiser_densmatr_initUniformlyRandomPureStateAmps(Qureg qureg) {
+    qbmap_canon(qureg);
     assert_localiserGivenDensMatr(qureg);
     bool wasMemAlloc = false;
     Qureg pure = makeScratchStateVecFor(qureg, wasMemAlloc);
@@ -385,6 +580,7 @@ void localiser_densmatr_initUniformlyRandomPureStateAmps(Qureg qureg) {
 }
 
 void localiser_densmatr_initMixtureOfUniformlyRandomPureStates(Qureg qureg, qindex numPureStates) {
+    qbmap_canon(qureg);
     assert_localiserGivenDensMatr(qureg);
     initBlankState(qureg);
     bool wasMemAlloc = false;
@@ -437,7 +633,7 @@ static void swapPrefixWithSuffix(Qureg qureg, vector<int> ctrls, vector<int> ctr
     accel_statevec_anyCtrlSwap_subC(qureg, ctrls, ctrlStates, suffixTarg, suffixState);
 }
 
-void localiser_statevec_anyCtrlSwap(Qureg qureg, vector<int> ctrls, vector<int> ctrlStates, int targ1, int targ2) {
+static void phys_statevec_anyCtrlSwap(Qureg qureg, vector<int> ctrls, vector<int> ctrlStates, int targ1, int targ2) {
     if (targ1 > targ2)
         std::swap(targ1, targ2);
     if (!localiseCtrls(qureg, ctrls, ctrlStates))
@@ -465,7 +661,7 @@ static void multiSwapPrefixWithSuffix(Qureg qureg, vector<int> targsA, vector<in
  * DENSE MATRICES (localiser.cpp:941-1082)
  */
 
-void localiser_statevec_anyCtrlOneTargDenseMatr(Qureg qureg, vector<int> ctrls, vector<int> ctrlStates, int targ, CompMatr1 matr, bool conj) {
+static void phys_statevec_anyCtrlOneTargDenseMatr(Qureg qureg, vector<int> ctrls, vector<int> ctrlStates, int targ, CompMatr1 matr, bool conj) {
     if (!localiseCtrls(qureg, ctrls, ctrlStates))
         return;
     if (conj)
@@ -552,15 +748,15 @@ static void denseTwoOrMoreTargs(Qureg qureg, vector<int> ctrls, vector<int> ctrl
     multiSwapPrefixWithSuffix(qureg, targs, newTargs);
 }
 
-void localiser_statevec_anyCtrlTwoTargDenseMatr(Qureg qureg, vector<int> ctrls, vector<int> ctrlStates, int targ1, int targ2, CompMatr2 matr, bool conj) {
+static void phys_statevec_anyCtrlTwoTargDenseMatr(Qureg qureg, vector<int> ctrls, vector<int> ctrlStates, int targ1, int targ2, CompMatr2 matr, bool conj) {
     denseTwoOrMoreTargs(qureg, ctrls, ctrlStates, {targ1, targ2}, matr, conj);
 }
 
-void localiser_statevec_anyCtrlAnyTargDenseMatr(Qureg qureg, vector<int> ctrls, vector<int> ctrlStates, vector<int> targs, CompMatr matr, bool conj) {
+static void phys_statevec_anyCtrlAnyTargDenseMatr(Qureg qureg, vector<int> ctrls, vector<int> ctrlStates, vector<int> targs, CompMatr matr, bool conj) {
     if (targs.size() == 1)
-        localiser_statevec_anyCtrlOneTargDenseMatr(qureg, ctrls, ctrlStates, targs[0], getCompMatr1(matr.cpuElems), conj);
+        phys_statevec_anyCtrlOneTargDenseMatr(qureg, ctrls, ctrlStates, targs[0], getCompMatr1(matr.cpuElems), conj);
     else if (targs.size() == 2)
-        localiser_statevec_anyCtrlTwoTargDenseMatr(qureg, ctrls, ctrlStates, targs[0], targs[1], getCompMatr2(matr.cpuElems), conj);
+        phys_statevec_anyCtrlTwoTargDenseMatr(qureg, ctrls, ctrlStates, targs[0], targs[1], getCompMatr2(matr.cpuElems), conj);
     else
         denseTwoOrMoreTargs(qureg, ctrls, ctrlStates, targs, matr, conj);
 }
@@ -570,7 +766,7 @@ void localiser_statevec_anyCtrlAnyTargDenseMatr(Qureg qureg, vector<int> ctrls, 
  * DIAGONAL MATRICES (localiser.cpp:1089-1207): never communicate; prefix targets read the rank inside the kernel
  */
 
-void localiser_statevec_anyCtrlOneTargDiagMatr(Qureg qureg, vector<int> ctrls, vector<int> ctrlStates, int targ, DiagMatr1 matr, bool conj) {
+static void phys_statevec_anyCtrlOneTargDiagMatr(Qureg qureg, vector<int> ctrls, vector<int> ctrlStates, int targ, DiagMatr1 matr, bool conj) {
     if (!localiseCtrls(qureg, ctrls, ctrlStates))
         return;
     if (conj)
@@ -578,7 +774,7 @@ void localiser_statevec_anyCtrlOneTargDiagMatr(Qureg qureg, vector<int> ctrls, v
     accel_statevec_anyCtrlOneTargDiagMatr_sub(qureg, ctrls, ctrlStates, targ, matr);
 }
 
-void localiser_statevec_anyCtrlTwoTargDiagMatr(Qureg qureg, vector<int> ctrls, vector<int> ctrlStates, int targ1, int targ2, DiagMatr2 matr, bool conj) {
+static void phys_statevec_anyCtrlTwoTargDiagMatr(Qureg qureg, vector<int> ctrls, vector<int> ctrlStates, int targ1, int targ2, DiagMatr2 matr, bool conj) {
     if (!localiseCtrls(qureg, ctrls, ctrlStates))
         return;
     if (conj)
@@ -586,13 +782,14 @@ void localiser_statevec_anyCtrlTwoTargDiagMatr(Qureg qureg, vector<int> ctrls, v
     accel_statevec_anyCtrlTwoTargDiagMatr_sub(qureg, ctrls, ctrlStates, targ1, targ2, matr);
 }
 
-void localiser_statevec_anyCtrlAnyTargDiagMatr(Qureg qureg, vector<int> ctrls, vector<int> ctrlStates, vector<int> targs, DiagMatr matr, qcomp exponent, bool conj) {
+static void phys_statevec_anyCtrlAnyTargDiagMatr(Qureg qureg, vector<int> ctrls, vector<int> ctrlStates, vector<int> targs, DiagMatr matr, qcomp exponent, bool conj) {
     if (!localiseCtrls(qureg, ctrls, ctrlStates))
         return;
     accel_statevec_anyCtrlAnyTargDiagMatr_sub(qureg, ctrls, ctrlStates, targs, matr, exponent, conj);
 }
 
 void localiser_statevec_allTargDiagMatr(Qureg qureg, FullStateDiagMatr matr, qcomp exponent) {
+    qbmap_canon(qureg);
     assert_localiserGivenStateVec(qureg);
     if (!qureg.isDistributed && matr.isDistributed)
         error_localiserGivenDistribMatrixAndLocalQureg();
@@ -603,6 +800,7 @@ void localiser_statevec_allTargDiagMatr(Qureg qureg, FullStateDiagMatr matr, qco
 }
 
 void localiser_densmatr_allTargDiagMatr(Qureg qureg, FullStateDiagMatr matr, qcomp exponent, bool multiplyOnly) {
+    qbmap_canon(qureg);
     assert_localiserGivenDensMatr(qureg);
     if (!qureg.isDistributed && matr.isDistributed) {
         error_localiserGivenDistribMatrixAndLocalQureg();
@@ -618,12 +816,15 @@ void localiser_densmatr_allTargDiagMatr(Qureg qureg, FullStateDiagMatr matr, qco
 
 template <class T>
 void localiser_statevec_anyCtrlAnyTargAnyMatr(Qureg qureg, vector<int> ctrls, vector<int> ctrlStates, vector<int> targs, T matr, bool conj) {
-    if constexpr (util_isDiagMatr <T>()) localiser_statevec_anyCtrlAnyTargDiagMatr(qureg,  ctrls, ctrlStates, targs, matr, 1, conj);
-    if constexpr (util_isDiagMatr1<T>()) localiser_statevec_anyCtrlOneTargDiagMatr(qureg,  ctrls, ctrlStates, targs[0], matr, conj);
-    if constexpr (util_isDiagMatr2<T>()) localiser_statevec_anyCtrlTwoTargDiagMatr(qureg,  ctrls, ctrlStates, targs[0], targs[1], matr, conj);
-    if constexpr (util_isCompMatr <T>()) localiser_statevec_anyCtrlAnyTargDenseMatr(qureg, ctrls, ctrlStates, targs, matr, conj);
-    if constexpr (util_isCompMatr1<T>()) localiser_statevec_anyCtrlOneTargDenseMatr(qureg, ctrls, ctrlStates, targs[0], matr, conj);
-    if constexpr (util_isCompMatr2<T>()) localiser_statevec_anyCtrlTwoTargDenseMatr(qureg, ctrls, ctrlStates, targs[0], targs[1], matr, conj);
+    if constexpr (util_isCompMatr<T>() || util_isCompMatr1<T>() || util_isCompMatr2<T>())
+        relabelForDenseGate(qureg, ctrls, targs);
+    else { QubitMap* m = findMap(qureg); mapQubits(m, ctrls); mapQubits(m, targs); }
+    if constexpr (util_isDiagMatr <T>()) phys_statevec_anyCtrlAnyTargDiagMatr(qureg,  ctrls, ctrlStates, targs, matr, 1, conj);
+    if constexpr (util_isDiagMatr1<T>()) phys_statevec_anyCtrlOneTargDiagMatr(qureg,  ctrls, ctrlStates, targs[0], matr, conj);
+    if constexpr (util_isDiagMatr2<T>()) phys_statevec_anyCtrlTwoTargDiagMatr(qureg,  ctrls, ctrlStates, targs[0], targs[1], matr, conj);
+    if constexpr (util_isCompMatr <T>()) phys_statevec_anyCtrlAnyTargDenseMatr(qureg, ctrls, ctrlStates, targs, matr, conj);
+    if constexpr (util_isCompMatr1<T>()) phys_statevec_anyCtrlOneTargDenseMatr(qureg, ctrls, ctrlStates, targs[0], matr, conj);
+    if constexpr (util_isCompMatr2<T>()) phys_statevec_anyCtrlTwoTargDenseMatr(qureg, ctrls, ctrlStates, targs[0], targs[1], matr, conj);
 }
 
 template void localiser_statevec_anyCtrlAnyTargAnyMatr(Qureg, vector<int>, vector<int>, vector<int>, DiagMatr,  bool);
@@ -680,7 +881,7 @@ static void pauliTensorOrGadget(Qureg qureg, vector<int> ctrls, vector<int> ctrl
     accel_statevector_anyCtrlPauliTensorOrGadget_subB(qureg, ctrls, ctrlStates, suffixX, suffixY, suffixZ, ampFac, pairAmpFac, bufferMaskXY);
 }
 
-void localiser_statevec_anyCtrlPauliTensor(Qureg qureg, vector<int> ctrls, vector<int> ctrlStates, PauliStr str, qcomp factor) {
+static void phys_statevec_anyCtrlPauliTensor(Qureg qureg, vector<int> ctrls, vector<int> ctrlStates, PauliStr str, qcomp factor) {
     if (paulis_containsXOrY(str)) {
         pauliTensorOrGadget(qureg, ctrls, ctrlStates, str, 0 * factor, 1 * factor);
     } else {
@@ -690,13 +891,13 @@ void localiser_statevec_anyCtrlPauliTensor(Qureg qureg, vector<int> ctrls, vecto
     }
 }
 
-void localiser_statevec_anyCtrlPhaseGadget(Qureg qureg, vector<int> ctrls, vector<int> ctrlStates, vector<int> targs, qreal phase) {
+static void phys_statevec_anyCtrlPhaseGadget(Qureg qureg, vector<int> ctrls, vector<int> ctrlStates, vector<int> targs, qreal phase) {
     zTensorOrGadget(qureg, ctrls, ctrlStates, targs, true, phase);
 }
 
-void localiser_statevec_anyCtrlPauliGadget(Qureg qureg, vector<int> ctrls, vector<int> ctrlStates, PauliStr str, qreal phase) {
+static void phys_statevec_anyCtrlPauliGadget(Qureg qureg, vector<int> ctrls, vector<int> ctrlStates, PauliStr str, qreal phase) {
     if (!paulis_containsXOrY(str)) {
-        localiser_statevec_anyCtrlPhaseGadget(qureg, ctrls, ctrlStates, paulis_getInds(str), phase);
+        phys_statevec_anyCtrlPhaseGadget(qureg, ctrls, ctrlStates, paulis_getInds(str), phase);
         return;
     }
     qcomp ampFac     = std::cos(phase);
@@ -710,6 +911,7 @@ void localiser_statevec_anyCtrlPauliGadget(Qureg qureg, vector<int> ctrls, vecto
  */
 
 void localiser_statevec_setQuregToSuperposition(qcomp facOut, Qureg outQureg, qcomp fac1, Qureg inQureg1, qcomp fac2, Qureg inQureg2) {
+    qbmap_canon(outQureg); qbmap_canon(inQureg1); qbmap_canon(inQureg2);
     accel_statevec_setQuregToSuperposition_sub(facOut, outQureg, fac1, inQureg1, fac2, inQureg2);
 }
 
@@ -729,6 +931,7 @@ static void mixDensityMatrixWithStatevector(qreal outProb, Qureg out, qreal inPr
 }
 
 void localiser_densmatr_mixQureg(qreal outProb, Qureg out, qreal inProb, Qureg in) {
+    qbmap_canon(out); qbmap_canon(in);
     assert_localiserGivenDensMatr(out);
     (in.isDensityMatrix)?
         accel_densmatr_mixQureg_subA(outProb, out, inProb, in):
@@ -742,6 +945,7 @@ void localiser_densmatr_mixQureg(qreal outProb, Qureg out, qreal inProb, Qureg i
  */
 
 void localiser_densmatr_oneQubitDephasing(Qureg qureg, int qubit, qreal prob) {
+    qbmap_canon(qureg);
     assert_localiserGivenDensMatr(qureg);
     (braIsPrefix(qureg, qubit))?
         accel_densmatr_oneQubitDephasing_subB(qureg, qubit, prob):
@@ -749,6 +953,7 @@ void localiser_densmatr_oneQubitDephasing(Qureg qureg, int qubit, qreal prob) {
 }
 
 void localiser_densmatr_twoQubitDephasing(Qureg qureg, int qubit1, int qubit2, qreal prob) {
+    qbmap_canon(qureg);
     assert_localiserGivenDensMatr(qureg);
     (braIsPrefix(qureg, std::max(qubit1, qubit2)))?
         accel_densmatr_twoQubitDephasing_subB(qureg, qubit1, qubit2, prob):
@@ -756,6 +961,7 @@ void localiser_densmatr_twoQubitDephasing(Qureg qureg, int qubit1, int qubit2, q
 }
 
 void localiser_densmatr_oneQubitDepolarising(Qureg qureg, int qubit, qreal prob) {
+    qbmap_canon(qureg);
     assert_localiserGivenDensMatr(qureg);
     if (!braIsPrefix(qureg, qubit)) {
         accel_densmatr_oneQubitDepolarising_subA(qureg, qubit, prob);
@@ -768,6 +974,7 @@ void localiser_densmatr_oneQubitDepolarising(Qureg qureg, int qubit, qreal prob)
 }
 
 void localiser_densmatr_twoQubitDepolarising(Qureg qureg, int qubit1, int qubit2, qreal prob) {
+    qbmap_canon(qureg);
     assert_localiserGivenDensMatr(qureg);
     if (qubit1 > qubit2)
         std::swap(qubit1, qubit2);
@@ -807,6 +1014,7 @@ void localiser_densmatr_twoQubitDepolarising(Qureg qureg, int qubit1, int qubit2
 }
 
 void localiser_densmatr_oneQubitPauliChannel(Qureg qureg, int qubit, qreal probX, qreal probY, qreal probZ) {
+    qbmap_canon(qureg);
     assert_localiserGivenDensMatr(qureg);
     qreal probI = 1 - probX - probY - probZ;
     if (!braIsPrefix(qureg, qubit)) {
@@ -818,6 +1026,7 @@ void localiser_densmatr_oneQubitPauliChannel(Qureg qureg, int qubit, qreal probX
 }
 
 void localiser_densmatr_oneQubitDamping(Qureg qureg, int qubit, qreal prob) {
+    qbmap_canon(qureg);
     assert_localiserGivenDensMatr(qureg);
     if (!braIsPrefix(qureg, qubit)) {
         accel_densmatr_oneQubitDamping_subA(qureg, qubit, prob);
@@ -845,6 +1054,7 @@ void localiser_densmatr_oneQubitDamping(Qureg qureg, int qubit, qreal prob) {
  */
 
 void localiser_densmatr_superoperator(Qureg qureg, SuperOp op, vector<int> ketTargs) {
+    qbmap_canon(qureg);
     assert_localiserGivenDensMatr(qureg);
     CompMatr matr;
     matr.numQubits = 2 * op.numQubits;
@@ -856,10 +1066,11 @@ void localiser_densmatr_superoperator(Qureg qureg, SuperOp op, vector<int> ketTa
     matr.cpuElemsFlat = op.cpuElemsFlat;
     matr.gpuElemsFlat = op.gpuElemsFlat;
     auto allTargs = util_getConcatenated(ketTargs, util_getBraQubits(ketTargs, qureg));
-    localiser_statevec_anyCtrlAnyTargDenseMatr(qureg, {}, {}, allTargs, matr, false);
+    phys_statevec_anyCtrlAnyTargDenseMatr(qureg, {}, {}, allTargs, matr, false);
 }
 
 void localiser_densmatr_krausMap(Qureg qureg, KrausMap map, vector<int> ketTargs) {
+    qbmap_canon(qureg);
     localiser_densmatr_superoperator(qureg, map.superop, ketTargs);
 }
 
@@ -906,6 +1117,7 @@ static vector<int> orderOfSurvivingQubits(Qureg qureg, vector<int> originalTargs
 }
 
 void localiser_densmatr_partialTrace(Qureg inQureg, Qureg outQureg, vector<int> targs) {
+    qbmap_canon(inQureg); qbmap_canon(outQureg);
     assert_localiserPartialTraceGivenCompatibleQuregs(inQureg, outQureg, targs.size());
     auto ketTargs = util_getSorted(targs);
     auto braTargs = util_getBraQubits(ketTargs, inQureg);
@@ -929,7 +1141,7 @@ void localiser_densmatr_partialTrace(Qureg inQureg, Qureg outQureg, vector<int> 
         int pair = 0;
         while (remaining[pair] != qubit)
             pair++;
-        localiser_statevec_anyCtrlSwap(outQureg, {}, {}, qubit, pair);
+        phys_statevec_anyCtrlSwap(outQureg, {}, {}, qubit, pair);
         std::swap(remaining[qubit], remaining[pair]);
     }
     multiSwapPrefixWithSuffix(inQureg, sufTargs, allTargs);
@@ -948,6 +1160,7 @@ qreal localiser_statevec_calcTotalProb(Qureg qureg) {
 }
 
 qreal localiser_densmatr_calcTotalProb(Qureg qureg) {
+    qbmap_canon(qureg);
     assert_localiserGivenDensMatr(qureg);
     qreal prob = accel_densmatr_calcTotalProb_sub(qureg);
     if (qureg.isDistributed)
@@ -955,7 +1168,7 @@ qreal localiser_densmatr_calcTotalProb(Qureg qureg) {
     return prob;
 }
 
-qreal localiser_statevec_calcProbOfMultiQubitOutcome(Qureg qureg, vector<int> qubits, vector<int> outcomes) {
+static qreal phys_statevec_calcProbOfMultiQubitOutcome(Qureg qureg, vector<int> qubits, vector<int> outcomes) {
     assert_localiserGivenStateVec(qureg);
     qreal prob = 0;
     if (prefixValuesMatch(qureg, qubits, outcomes)) {
@@ -969,6 +1182,7 @@ qreal localiser_statevec_calcProbOfMultiQubitOutcome(Qureg qureg, vector<int> qu
 }
 
 qreal localiser_densmatr_calcProbOfMultiQubitOutcome(Qureg qureg, vector<int> qubits, vector<int> outcomes) {
+    qbmap_canon(qureg);
     assert_localiserGivenDensMatr(qureg);
     qreal prob = 0;
     auto braQubits = util_getBraQubits(qubits, qureg);
@@ -987,6 +1201,7 @@ qreal localiser_densmatr_calcProbOfMultiQubitOutcome(Qureg qureg, vector<int> qu
 }
 
 void localiser_statevec_calcProbsOfAllMultiQubitOutcomes(qreal* outProbs, Qureg qureg, vector<int> qubits) {
+    qbmap_canon(qureg);
     assert_localiserGivenStateVec(qureg);
     accel_statevec_calcProbsOfAllMultiQubitOutcomes_sub(outProbs, qureg, qubits);
     if (qureg.isDistributed)
@@ -994,6 +1209,7 @@ void localiser_statevec_calcProbsOfAllMultiQubitOutcomes(qreal* outProbs, Qureg 
 }
 
 void localiser_densmatr_calcProbsOfAllMultiQubitOutcomes(qreal* outProbs, Qureg qureg, vector<int> qubits) {
+    qbmap_canon(qureg);
     assert_localiserGivenDensMatr(qureg);
     accel_densmatr_calcProbsOfAllMultiQubitOutcomes_sub(outProbs, qureg, qubits);
     if (qureg.isDistributed)
@@ -1023,6 +1239,7 @@ static qcomp expecDensMatrPauliStrLocal(Qureg qureg, PauliStr str) {
 }
 
 qcomp localiser_statevec_calcExpecPauliStr(Qureg qureg, PauliStr str) {
+    qbmap_canon(qureg);
     assert_localiserGivenStateVec(qureg);
     auto [targsX, targsY, targsZ] = paulis_getSeparateInds(str, qureg);
     auto [prefixX, suffixX] = util_getPrefixAndSuffixQubits(targsX, qureg);
@@ -1043,6 +1260,7 @@ qcomp localiser_statevec_calcExpecPauliStr(Qureg qureg, PauliStr str) {
 }
 
 qcomp localiser_densmatr_calcExpecPauliStr(Qureg qureg, PauliStr str) {
+    qbmap_canon(qureg);
     assert_localiserGivenDensMatr(qureg);
     qcomp value = expecDensMatrPauliStrLocal(qureg, str);
     if (qureg.isDistributed)
@@ -1051,6 +1269,7 @@ qcomp localiser_densmatr_calcExpecPauliStr(Qureg qureg, PauliStr str) {
 }
 
 qcomp localiser_statevec_calcExpecPauliStrSum(Qureg qureg, PauliStrSum sum) {
+    qbmap_canon(qureg);
     assert_localiserGivenStateVec(qureg);
 
     // terms whose PREFIX X/Y pattern coincides need the same partner rank: one exchange serves the whole group
@@ -1112,6 +1331,7 @@ qcomp localiser_statevec_calcExpecPauliStrSum(Qureg qureg, PauliStrSum sum) {
 }
 
 qcomp localiser_densmatr_calcExpecPauliStrSum(Qureg qureg, PauliStrSum sum) {
+    qbmap_canon(qureg);
     assert_localiserGivenDensMatr(qureg);
     qcomp value = 0;
     for (qindex t = 0; t < sum.numTerms; t++)
@@ -1122,6 +1342,7 @@ qcomp localiser_densmatr_calcExpecPauliStrSum(Qureg qureg, PauliStrSum sum) {
 }
 
 qcomp localiser_statevec_calcExpecFullStateDiagMatr(Qureg qureg, FullStateDiagMatr matr, qcomp exponent, bool useRealPow) {
+    qbmap_canon(qureg);
     auto [quregSpoof, matrSpoof] = withMatchingDistributions(qureg, matr);
     qcomp value = accel_statevec_calcExpecFullStateDiagMatr_sub(quregSpoof, matrSpoof, exponent, useRealPow);
     if (quregSpoof.isDistributed)
@@ -1130,6 +1351,7 @@ qcomp localiser_statevec_calcExpecFullStateDiagMatr(Qureg qureg, FullStateDiagMa
 }
 
 qcomp localiser_densmatr_calcExpecFullStateDiagMatr(Qureg qureg, FullStateDiagMatr matr, qcomp exponent, bool useRealPow) {
+    qbmap_canon(qureg);
     auto [quregSpoof, matrSpoof] = withMatchingDistributions(qureg, matr);
     qcomp value = accel_densmatr_calcExpecFullStateDiagMatr_sub(quregSpoof, matrSpoof, exponent, useRealPow);
     if (quregSpoof.isDistributed)
@@ -1143,6 +1365,7 @@ qcomp localiser_densmatr_calcExpecFullStateDiagMatr(Qureg qureg, FullStateDiagMa
  */
 
 qcomp localiser_statevec_calcInnerProduct(Qureg quregA, Qureg quregB) {
+    qbmap_canon(quregA); qbmap_canon(quregB);
     Qureg a = quregA, b = quregB;
     if (quregA.isDistributed != quregB.isDistributed) {
         a = (quregA.isDistributed)? quregA : viewLocalAsDistributed(quregA, quregB);
@@ -1155,6 +1378,7 @@ qcomp localiser_statevec_calcInnerProduct(Qureg quregA, Qureg quregB) {
 }
 
 qcomp localiser_densmatr_calcFidelityWithPureState(Qureg rho, Qureg psi, bool conj) {
+    qbmap_canon(rho); qbmap_canon(psi);
     assert_localiserGivenDensMatr(rho);
     assert_localiserGivenStateVec(psi);
     qcomp fid = 0;
@@ -1172,6 +1396,7 @@ qcomp localiser_densmatr_calcFidelityWithPureState(Qureg rho, Qureg psi, bool co
 }
 
 qreal localiser_densmatr_calcHilbertSchmidtDistance(Qureg quregA, Qureg quregB) {
+    qbmap_canon(quregA); qbmap_canon(quregB);
     assert_localiserGivenDensMatr(quregA);
     assert_localiserGivenDensMatr(quregB);
     Qureg a = quregA, b = quregB;
@@ -1190,7 +1415,7 @@ qreal localiser_densmatr_calcHilbertSchmidtDistance(Qureg quregA, Qureg quregB) 
  * PROJECTORS (localiser.cpp:2295-2322)
  */
 
-void localiser_statevec_multiQubitProjector(Qureg qureg, vector<int> qubits, vector<int> outcomes, qreal prob) {
+static void phys_statevec_multiQubitProjector(Qureg qureg, vector<int> qubits, vector<int> outcomes, qreal prob) {
     assert_localiserGivenStateVec(qureg);
     if (!prefixValuesMatch(qureg, qubits, outcomes)) {
         accel_statevec_initUniformState_sub(qureg, 0);     // this rank's prefix bits contradict the outcome
@@ -1204,6 +1429,90 @@ void localiser_statevec_multiQubitProjector(Qureg qureg, vector<int> qubits, vec
 }
 
 void localiser_densmatr_multiQubitProjector(Qureg qureg, vector<int> qubits, vector<int> outcomes, qreal prob) {
+    qbmap_canon(qureg);
     assert_localiserGivenDensMatr(qureg);
     accel_densmatr_multiQubitProjector_sub(qureg, qubits, outcomes, prob);
+}
+
+
+/*
+ * RELABELLING-AWARE PUBLIC ENTRY POINTS: translate logical qubits to index bits (see LAZY QUBIT RELABELLING),
+ * then run the physical implementation above
+ */
+
+void localiser_statevec_anyCtrlSwap(Qureg qureg, vector<int> ctrls, vector<int> ctrlStates, int targ1, int targ2) {
+    if (ctrls.empty() && mapEligible(qureg)) {              // pure relabelling: no amplitude moves
+        QubitMap& m = getMap(qureg);
+        relabelSwap(m, targ1, targ2);
+        return;
+    }
+    QubitMap* m = findMap(qureg);
+    mapQubits(m, ctrls);
+    phys_statevec_anyCtrlSwap(qureg, ctrls, ctrlStates, mapQubit(m, targ1), mapQubit(m, targ2));
+}
+
+void localiser_statevec_anyCtrlOneTargDenseMatr(Qureg qureg, vector<int> ctrls, vector<int> ctrlStates, int targ, CompMatr1 matr, bool conj) {
+    vector<int> targs = {targ};
+    relabelForDenseGate(qureg, ctrls, targs);
+    phys_statevec_anyCtrlOneTargDenseMatr(qureg, ctrls, ctrlStates, targs[0], matr, conj);
+}
+
+void localiser_statevec_anyCtrlTwoTargDenseMatr(Qureg qureg, vector<int> ctrls, vector<int> ctrlStates, int targ1, int targ2, CompMatr2 matr, bool conj) {
+    vector<int> targs = {targ1, targ2};
+    relabelForDenseGate(qureg, ctrls, targs);
+    phys_statevec_anyCtrlTwoTargDenseMatr(qureg, ctrls, ctrlStates, targs[0], targs[1], matr, conj);
+}
+
+void localiser_statevec_anyCtrlAnyTargDenseMatr(Qureg qureg, vector<int> ctrls, vector<int> ctrlStates, vector<int> targs, CompMatr matr, bool conj) {
+    relabelForDenseGate(qureg, ctrls, targs);
+    phys_statevec_anyCtrlAnyTargDenseMatr(qureg, ctrls, ctrlStates, targs, matr, conj);
+}
+
+void localiser_statevec_anyCtrlOneTargDiagMatr(Qureg qureg, vector<int> ctrls, vector<int> ctrlStates, int targ, DiagMatr1 matr, bool conj) {
+    QubitMap* m = findMap(qureg);
+    mapQubits(m, ctrls);
+    phys_statevec_anyCtrlOneTargDiagMatr(qureg, ctrls, ctrlStates, mapQubit(m, targ), matr, conj);
+}
+
+void localiser_statevec_anyCtrlTwoTargDiagMatr(Qureg qureg, vector<int> ctrls, vector<int> ctrlStates, int targ1, int targ2, DiagMatr2 matr, bool conj) {
+    QubitMap* m = findMap(qureg);
+    mapQubits(m, ctrls);
+    int t1 = mapQubit(m, targ1), t2 = mapQubit(m, targ2);
+    phys_statevec_anyCtrlTwoTargDiagMatr(qureg, ctrls, ctrlStates, t1, t2, matr, conj);
+}
+
+void localiser_statevec_anyCtrlAnyTargDiagMatr(Qureg qureg, vector<int> ctrls, vector<int> ctrlStates, vector<int> targs, DiagMatr matr, qcomp exponent, bool conj) {
+    QubitMap* m = findMap(qureg);
+    mapQubits(m, ctrls);
+    mapQubits(m, targs);
+    phys_statevec_anyCtrlAnyTargDiagMatr(qureg, ctrls, ctrlStates, targs, matr, exponent, conj);
+}
+
+void localiser_statevec_anyCtrlPauliTensor(Qureg qureg, vector<int> ctrls, vector<int> ctrlStates, PauliStr str, qcomp factor) {
+    QubitMap* m = findMap(qureg);
+    mapQubits(m, ctrls);
+    phys_statevec_anyCtrlPauliTensor(qureg, ctrls, ctrlStates, mapPauliStr(m, str), factor);
+}
+
+void localiser_statevec_anyCtrlPhaseGadget(Qureg qureg, vector<int> ctrls, vector<int> ctrlStates, vector<int> targs, qreal phase) {
+    QubitMap* m = findMap(qureg);
+    mapQubits(m, ctrls);
+    mapQubits(m, targs);
+    phys_statevec_anyCtrlPhaseGadget(qureg, ctrls, ctrlStates, targs, phase);
+}
+
+void localiser_statevec_anyCtrlPauliGadget(Qureg qureg, vector<int> ctrls, vector<int> ctrlStates, PauliStr str, qreal phase) {
+    QubitMap* m = findMap(qureg);
+    mapQubits(m, ctrls);
+    phys_statevec_anyCtrlPauliGadget(qureg, ctrls, ctrlStates, mapPauliStr(m, str), phase);
+}
+
+qreal localiser_statevec_calcProbOfMultiQubitOutcome(Qureg qureg, vector<int> qubits, vector<int> outcomes) {
+    mapQubits(findMap(qureg), qubits);
+    return phys_statevec_calcProbOfMultiQubitOutcome(qureg, qubits, outcomes);
+}
+
+void localiser_statevec_multiQubitProjector(Qureg qureg, vector<int> qubits, vector<int> outcomes, qreal prob) {
+    mapQubits(findMap(qureg), qubits);
+    phys_statevec_multiQubitProjector(qureg, qubits, outcomes, prob);
 }

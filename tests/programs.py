@@ -289,3 +289,61 @@ def measurement_program(n, seed):
         ops.append(["applyQubitMeasurement", "psi", q])
     ops.append(["calcTotalProb", "psi"])
     return {"seeds": [int(seed), 7], "quregs": {"psi": {"n": n, "init": "zero"}}, "ops": ops, "dump": ["psi"]}
+
+
+def relabel_program(n, seed, num_ops=160):
+    """Stress of the lazy qubit relabelling (quest_b200/shim/localiser_b200.cpp): uncontrolled SWAPs (pure relabelling)
+    and dense gates on every qubit (on several GPUs: targets on rank bits, pulled into the shard and left there)
+    interleaved with the relabelling-aware gates and reductions, and with operations that must first restore the
+    canonical order (expectation values, full-state diagonals, amplitude reads at the end)."""
+    rng = np.random.default_rng(seed)
+    ops = []
+    for _ in range(num_ops):
+        r = int(rng.integers(14))
+        if r < 3:
+            a, b = _pick(rng, n, 2)
+            ops.append(["applySwap", "psi", a, b])
+        elif r < 5:
+            ops.append(["applyCompMatr1", "psi", int(rng.integers(n)), {"m1": enc_mat(rand_unitary(rng, 2))}])
+        elif r < 7:
+            a, b = _pick(rng, n, 2)
+            ops.append(["applyCompMatr2", "psi", a, b, {"m2": enc_mat(rand_unitary(rng, 4))}])
+        elif r == 7:
+            c, s, t = _ctrl_targ(rng, n, 1, 2)
+            ops.append(["applyMultiStateControlledCompMatr2", "psi", c, s, 1, t[0], t[1], {"m2": enc_mat(rand_unitary(rng, 4))}])
+        elif r == 8:
+            nt = min(3, n)
+            ops.append(["applyCompMatr", "psi", _pick(rng, n, nt), nt, {"m": enc_mat(rand_unitary(rng, 1 << nt))}])
+        elif r == 9:
+            a, b = _pick(rng, n, 2)
+            ops.append(["applyTwoQubitPhaseShift", "psi", a, b, float(rng.uniform(0, 6))])
+            ops.append(["applyDiagMatr1", "psi", int(rng.integers(n)), {"d1": enc_mat(rand_diag_unitary(rng, 2))}])
+        elif r == 10:
+            k = int(rng.integers(1, min(n, 4) + 1))
+            chars, qs = _pauli(rng, n, k)
+            ops.append(["applyPauliGadget", "psi", {"pauli": [chars, qs]}, float(rng.uniform(-3, 3))])
+            chars, qs = _pauli(rng, n, k)
+            ops.append(["applyPauliStr", "psi", {"pauli": [chars, qs]}])
+        elif r == 11:
+            k = int(rng.integers(1, min(n, 3) + 1))
+            ops.append(["applyPhaseGadget", "psi", _pick(rng, n, k), k, float(rng.uniform(-3, 3))])
+            c, s, t = _ctrl_targ(rng, n, 1, 2)
+            ops.append(["applyMultiStateControlledSwap", "psi", c, s, 1, t[0], t[1]])
+        elif r == 12:
+            ops.append(["calcProbOfQubitOutcome", "psi", int(rng.integers(n)), int(rng.integers(2))])
+            qs = _pick(rng, n, 2)
+            ops.append(["calcProbOfMultiQubitOutcome", "psi", qs, [int(b) for b in rng.integers(0, 2, size=2)], 2])
+        else:
+            which = int(rng.integers(4))
+            if which == 0:
+                chars, qs = _pauli(rng, n, min(n, 3))
+                ops.append(["calcExpecPauliStr", "psi", {"pauli": [chars, qs]}])
+            elif which == 1:
+                ops.append(["calcProbsOfAllMultiQubitOutcomes", {"out_reals": 4}, "psi", _pick(rng, n, 2), 2])
+            elif which == 2:
+                ops.append(["applyFullStateDiagMatr", "psi", {"fsd": enc_mat(rand_diag_unitary(rng, 1 << n))}])
+            else:
+                ops.append(["applyMultiQubitProjector", "psi", _pick(rng, n, 1), [int(rng.integers(2))], 1])
+                ops.append(["calcTotalProb", "psi"])
+    ops.append(["calcTotalProb", "psi"])
+    return {"quregs": {"psi": {"n": n, "init": ["amps", enc_mat(rand_state(rng, n))]}}, "ops": ops, "dump": ["psi"]}

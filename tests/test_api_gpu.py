@@ -46,6 +46,11 @@ def test_live_calcs_and_channels():
     _live([P.calcs_program_sv(14, 4101), P.channels_program_dm(7, 4102), P.measurement_program(12, 4103)])
 
 
+def test_live_lazy_qubit_relabelling():
+    """SWAP relabelling + restoring the canonical order where an operation needs it (single GPU: no rank bits)"""
+    _live([P.relabel_program(6, 4201), P.relabel_program(14, 4202), P.relabel_program(17, 4203, num_ops=120)])
+
+
 def test_live_cfg1_20q():
     """BASELINE cfg 1 exactly: 20 qubits, H layer + 200 random {H, CNOT, RotateX, CompMatr1}"""
     _live([P.cfg1_program(20, 12345, 200)])

@@ -42,6 +42,17 @@ def test_statevector_gates_sharded(world, p2p):
 
 @pytest.mark.skipif(not WORLDS, reason="needs >= 2 GPUs")
 @pytest.mark.parametrize("world", WORLDS)
+@pytest.mark.parametrize("p2p", ["1", "0"], ids=["nvlink-p2p", "nccl-only"])
+def test_lazy_qubit_relabelling_sharded(world, p2p):
+    """dense gates on rank bits pull the qubit into the shard and leave it there; SWAPs only relabel; everything else
+    restores the canonical order first -- all invisible through the API"""
+    logp = world.bit_length() - 1
+    _check([P.relabel_program(logp + 3, 6301), P.relabel_program(logp + 7, 6302), P.relabel_program(logp + 13, 6303, num_ops=120)],
+           world, env={"QUEST_B200_P2P": p2p})
+
+
+@pytest.mark.skipif(not WORLDS, reason="needs >= 2 GPUs")
+@pytest.mark.parametrize("world", WORLDS)
 def test_calcs_measurement_sharded(world):
     logp = world.bit_length() - 1
     _check([P.calcs_program_sv(logp + 5, 6101), P.measurement_program(logp + 5, 6102), P.cfg5_program(logp + 6, 6103, num_terms=30),

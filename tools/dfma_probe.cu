@@ -99,7 +99,7 @@ int main() {
         cudaEventRecord(e0); kB<8><<<sms, threads>>>(out, in, iters); cudaEventRecord(e1); cudaEventSynchronize(e1);
         cudaEventElapsedTime(&ms, e0, e1); report("B: 8 chains, register operands", threads, (double)sms * threads * 8 * iters, ms);
     }
-    for (int threads : {256, 512}) {
+    for (int threads : {128, 256, 384, 512}) {
         float ms; const int iters = 2000;
         kC<<<sms, threads>>>(out, in, 10);
         cudaEventRecord(e0); kC<<<sms, threads>>>(out, in, iters); cudaEventRecord(e1); cudaEventSynchronize(e1);
