@@ -286,6 +286,7 @@ int qb_p2p_anyCtrlOneTargDenseMatr(const qb_state* q, const int* ctrls, const in
 /* SWAP of a prefix qubit (partner = pairRank) with suffix qubit suffixTarg: the half-shards whose suffix
  * bit differs from the rank bit trade places. (localiser.cpp:854-869 + gpu_subroutines.cpp:251-280) */
 int qb_p2p_swapHalves(const qb_state* q, int suffixTarg, int pairRank);
+int         qb_p2p_set_swap_mode(int mode);              /* half-shard swap: 1 (default) kernel push into the partner's buffer + local unpack; 2: copy engines; 0: in-place exchange kernel */
 
 #ifdef __cplusplus
 }

@@ -18,6 +18,7 @@
 #include <map>
 #include <vector>
 #include <string.h>
+#include <stdlib.h>
 
 int qb_comm_internal_allgather_host(const void* send, void* recvAll, size_t bytesPerRank);
 int qb_comm_internal_sendrecv_host(const void* send, void* recv, size_t bytes, int pairRank);
@@ -173,6 +174,53 @@ static void my_share(qindex total, int pairRank, qindex* first, qindex* count) {
     *count = low ? half : total - half;
 }
 
+// ---- half-shard swap through the partner's communication buffer -------------------------------------------
+// mode 1 (kernel push):  every GPU WRITES its outgoing half straight into the partner's buffer over NVLink (posted
+//   writes, no read round trips), the pair synchronises, and a local HBM-speed pass moves the received half from the
+//   own buffer into place.  mode 2 (copy-engine push): the same two steps issued as cudaMemcpy(2D)Async.
+// mode 0: the in-place exchange kernel (each GPU reads and writes half of the pairs remotely; no buffer needed).
+static int s_swapMode = -1;
+static int swap_mode() {
+    if (s_swapMode < 0) { const char* e = getenv("QUEST_B200_SWAP_MODE"); s_swapMode = e ? atoi(e) : 1; if (s_swapMode < 0 || s_swapMode > 2) s_swapMode = 1; }
+    return s_swapMode;
+}
+
+template <int ITEMS, bool GATHER>      // GATHER: dst[n] = src[ins(n)] (pack + push);  else dst[ins(n)] = src[n] (unpack in place)
+__global__ void __launch_bounds__(QB_BLOCK) k_half_copy(cplx* __restrict__ dst, const cplx* __restrict__ src, qindex count, const BitIns ins) {
+    const qindex base = (qindex)blockIdx.x * (QB_BLOCK * ITEMS) + threadIdx.x;
+    cplx v[ITEMS];
+#pragma unroll
+    for (int j = 0; j < ITEMS; j++) {
+        const qindex n = base + (qindex)j * QB_BLOCK;
+        if (n < count) v[j] = GATHER ? src[ins(n)] : src[n];
+    }
+#pragma unroll
+    for (int j = 0; j < ITEMS; j++) {
+        const qindex n = base + (qindex)j * QB_BLOCK;
+        if (n < count) { if (GATHER) dst[n] = v[j]; else dst[ins(n)] = v[j]; }
+    }
+    if (GATHER) __threadfence_system();
+}
+
+// copies between the strided half "suffix bit s == bitVal" of `shard` and a compact array, with the copy engines
+static int dma_half_copy(cplx* compact, cplx* shard, qindex numAmps, int s, int bitVal, bool toCompact) {
+    const qindex run = (qindex)1 << s;                     // contiguous amplitudes per row
+    const qindex rows = numAmps / (2 * run);
+    cplx* strided = shard + (bitVal ? run : 0);
+    const size_t width = (size_t)run * sizeof(cplx), pitch = 2 * width;
+    if (rows <= 16 || pitch > ((size_t)1 << 30)) {
+        for (qindex r = 0; r < rows; r++) {
+            cplx* a = compact + r * run; cplx* b = strided + 2 * r * run;
+            QB_CUDA(cudaMemcpyAsync(toCompact ? a : b, toCompact ? b : a, width, cudaMemcpyDeviceToDevice, g_qb.stream));
+        }
+    } else {
+        if (toCompact) QB_CUDA(cudaMemcpy2DAsync(compact, width, strided, pitch, width, (size_t)rows, cudaMemcpyDeviceToDevice, g_qb.stream));
+        else           QB_CUDA(cudaMemcpy2DAsync(strided, pitch, compact, width, width, (size_t)rows, cudaMemcpyDeviceToDevice, g_qb.stream));
+    }
+    g_qb.launches += 1;
+    return 0;
+}
+
 extern "C" {
 
 int qb_p2p_is_available(void) {
@@ -201,18 +249,37 @@ int qb_p2p_swapHalves(const qb_state* q, int suffixTarg, int pairRank) {
     QB_READY(); QB_CHECK_STATE(q); QB_CHECK_SUFFIX(&suffixTarg, 1, q);
     QB_REQUIRE(qb_p2p_is_available(), "p2p path is not available");
     void* peer = nullptr;
-    int r = peer_pointer(q->amps, pairRank, &peer); if (r) return r;
     // my amplitudes with suffix bit == !myBit trade places with the partner's amplitudes with suffix bit == myBit,
     // where myBit is this rank's value of the prefix qubit: myBit = 1 iff rank > pairRank (they differ in that bit only)
     int myBit = qb_comm_rank() > pairRank ? 1 : 0;
     int st = !myBit;
-    P2POp op; op.ins = qb_make_ins(&suffixTarg, &st, 1, nullptr, nullptr, 0); op.peerXor = pow2(suffixTarg); op.bit = myBit;
-    op.m00 = op.m01 = op.m10 = op.m11 = mk(0, 0);
-    qindex first, count;
-    my_share(q->numAmpsPerNode / 2, pairRank, &first, &count);
-    r = pair_barrier(pairRank); if (r) return r;
-    r = launch_pair<1>((cplx*)q->amps, (cplx*)peer, first, count, op); if (r) return r;
-    return pair_barrier(pairRank);
+    const int mode = (q->buffer != nullptr && q->numAmpsPerNode >= 2) ? swap_mode() : 0;
+    int r;
+    if (mode == 0) {
+        r = peer_pointer(q->amps, pairRank, &peer); if (r) return r;
+        P2POp op; op.ins = qb_make_ins(&suffixTarg, &st, 1, nullptr, nullptr, 0); op.peerXor = pow2(suffixTarg); op.bit = myBit;
+        op.m00 = op.m01 = op.m10 = op.m11 = mk(0, 0);
+        qindex first, count;
+        my_share(q->numAmpsPerNode / 2, pairRank, &first, &count);
+        r = pair_barrier(pairRank); if (r) return r;
+        r = launch_pair<1>((cplx*)q->amps, (cplx*)peer, first, count, op); if (r) return r;
+        return pair_barrier(pairRank);
+    }
+    // through the buffers: element n of my outgoing half lands at element n of the partner's buffer, and the partner's
+    // element n (its half with suffix bit == myBit) belongs at my index ins(n) -- the place my own element n came from
+    r = peer_pointer(q->buffer, pairRank, &peer); if (r) return r;
+    const qindex half = q->numAmpsPerNode / 2;
+    const BitIns ins = qb_make_ins(&suffixTarg, &st, 1, nullptr, nullptr, 0);
+    constexpr int ITEMS = 4;
+    r = pair_barrier(pairRank); if (r) return r;                 // the partner's buffer is free, its stream is here too
+    if (mode == 2) { r = dma_half_copy((cplx*)peer, (cplx*)q->amps, q->numAmpsPerNode, suffixTarg, st, true); if (r) return r; }
+    else { k_half_copy<ITEMS, true><<<qb_grid(half, ITEMS), QB_BLOCK, 0, g_qb.stream>>>((cplx*)peer, (const cplx*)q->amps, half, ins); QB_LAUNCH_CHECK(); }
+    r = pair_barrier(pairRank); if (r) return r;                 // both halves have landed
+    if (mode == 2) { r = dma_half_copy((cplx*)q->buffer, (cplx*)q->amps, q->numAmpsPerNode, suffixTarg, st, false); if (r) return r; }
+    else { k_half_copy<ITEMS, false><<<qb_grid(half, ITEMS), QB_BLOCK, 0, g_qb.stream>>>((cplx*)q->amps, (const cplx*)q->buffer, half, ins); QB_LAUNCH_CHECK(); }
+    return 0;
 }
+
+int qb_p2p_set_swap_mode(int mode) { s_swapMode = (mode < 0 || mode > 2) ? 1 : mode; return 0; }
 
 } // extern "C"
