@@ -286,7 +286,10 @@ int qb_p2p_anyCtrlOneTargDenseMatr(const qb_state* q, const int* ctrls, const in
 /* SWAP of a prefix qubit (partner = pairRank) with suffix qubit suffixTarg: the half-shards whose suffix
  * bit differs from the rank bit trade places. (localiser.cpp:854-869 + gpu_subroutines.cpp:251-280) */
 int qb_p2p_swapHalves(const qb_state* q, int suffixTarg, int pairRank);
-int         qb_p2p_set_swap_mode(int mode);              /* half-shard swap: 1 (default) kernel push into the partner's buffer + local unpack; 2: copy engines; 0: in-place exchange kernel */
+int         qb_p2p_swapHalvesDeferred(const qb_state* q, int suffixTarg, int pairRank); /* same, but may overtake queued gates that do not touch suffixTarg (caller vouches none depends on the rank bit) */
+int         qb_queue_info(const qb_state* q, unsigned long long* touchedSuffixMask, unsigned long long* flushEpoch); /* deferred gates of q: count, suffix qubits they involve, flush counter */
+int         qb_p2p_set_swap_mode(int mode);              /* half-shard swap: 0 (default) in-place exchange kernel; 1: kernel push into the partner's buffer + local unpack; 2: copy engines (all within 10%: profiles/) */
+int         qb_p2p_stats(unsigned long long* numExchanges, unsigned long long* linkBytesPerDir); /* peer-memory exchanges issued by this rank so far, and the bytes each sent one way */
 
 #ifdef __cplusplus
 }

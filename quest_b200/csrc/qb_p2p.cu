@@ -34,6 +34,7 @@ static bool s_ready = false, s_enabled = true, s_triedInit = false;
 static unsigned long long* s_myFlags = nullptr;                       // [QB_P2P_MAX_RANKS] written by peers
 static unsigned long long* s_peerFlags[QB_P2P_MAX_RANKS] = {nullptr}; // mapped flag pages of every peer
 static unsigned long long s_epoch[QB_P2P_MAX_RANKS] = {0};
+static unsigned long long s_numExchanges = 0, s_linkBytesPerDir = 0;    // statistics (qb_p2p_stats)
 
 void qb_p2p_note_alloc(void* base, size_t bytes) { s_allocs[(uintptr_t)base] = Alloc{bytes, false}; }
 
@@ -181,7 +182,7 @@ static void my_share(qindex total, int pairRank, qindex* first, qindex* count) {
 // mode 0: the in-place exchange kernel (each GPU reads and writes half of the pairs remotely; no buffer needed).
 static int s_swapMode = -1;
 static int swap_mode() {
-    if (s_swapMode < 0) { const char* e = getenv("QUEST_B200_SWAP_MODE"); s_swapMode = e ? atoi(e) : 1; if (s_swapMode < 0 || s_swapMode > 2) s_swapMode = 1; }
+    if (s_swapMode < 0) { const char* e = getenv("QUEST_B200_SWAP_MODE"); s_swapMode = e ? atoi(e) : 0; if (s_swapMode < 0 || s_swapMode > 2) s_swapMode = 0; }
     return s_swapMode;
 }
 
@@ -240,13 +241,33 @@ int qb_p2p_anyCtrlOneTargDenseMatr(const qb_state* q, const int* ctrls, const in
     op.m00 = mk(m[0]); op.m01 = mk(m[1]); op.m10 = mk(m[2]); op.m11 = mk(m[3]);
     qindex first, count;
     my_share(q->numAmpsPerNode >> nc, pairRank, &first, &count);
+    s_numExchanges++; s_linkBytesPerDir += (unsigned long long)(q->numAmpsPerNode >> nc) * sizeof(cplx);
     r = pair_barrier(pairRank); if (r) return r;
     r = launch_pair<0>((cplx*)q->amps, (cplx*)peer, first, count, op); if (r) return r;
     return pair_barrier(pairRank);
 }
 
+static int swap_halves(const qb_state* q, int suffixTarg, int pairRank);
+
 int qb_p2p_swapHalves(const qb_state* q, int suffixTarg, int pairRank) {
     QB_READY(); QB_CHECK_STATE(q); QB_CHECK_SUFFIX(&suffixTarg, 1, q);
+    return swap_halves(q, suffixTarg, pairRank);
+}
+
+// The same swap, but allowed to OVERTAKE the gates still deferred in the queue: it runs now, they run later.  That
+// is only legal when every queued gate commutes with the swap -- none touches `suffixTarg` (checked here; otherwise
+// the queue is flushed first) and none depends on the rank bit being swapped (the caller's promise: it resolves
+// rank-bit controls and diagonal sites before they reach this library, so only it can know).
+int qb_p2p_swapHalvesDeferred(const qb_state* q, int suffixTarg, int pairRank) {
+    QB_READY_NOFLUSH(); QB_CHECK_STATE(q); QB_CHECK_SUFFIX(&suffixTarg, 1, q);
+    unsigned long long touched = 0;
+    int queued = qb_queue_info(q, &touched, nullptr);
+    if (queued == 0 || ((touched >> suffixTarg) & 1)) QB_FLUSH();      // (a queue of another state is flushed too: cheap and safe)
+    return swap_halves(q, suffixTarg, pairRank);
+}
+
+static int swap_halves(const qb_state* q, int suffixTarg, int pairRank) {
+    s_numExchanges++; s_linkBytesPerDir += (unsigned long long)q->numAmpsPerNode / 2 * sizeof(cplx);
     QB_REQUIRE(qb_p2p_is_available(), "p2p path is not available");
     void* peer = nullptr;
     // my amplitudes with suffix bit == !myBit trade places with the partner's amplitudes with suffix bit == myBit,
@@ -280,6 +301,12 @@ int qb_p2p_swapHalves(const qb_state* q, int suffixTarg, int pairRank) {
     return 0;
 }
 
-int qb_p2p_set_swap_mode(int mode) { s_swapMode = (mode < 0 || mode > 2) ? 1 : mode; return 0; }
+extern "C" int qb_p2p_stats(unsigned long long* numExchanges, unsigned long long* linkBytesPerDir) {
+    if (numExchanges) *numExchanges = s_numExchanges;
+    if (linkBytesPerDir) *linkBytesPerDir = s_linkBytesPerDir;
+    return 0;
+}
+
+extern "C" int qb_p2p_set_swap_mode(int mode) { s_swapMode = (mode < 0 || mode > 2) ? 0 : mode; return 0; }
 
 } // extern "C"

@@ -75,6 +75,7 @@ static qb_state s_qstate;                      // identity of the state the queu
 static bool s_qvalid = false;
 static int s_status = 0;
 static bool s_inFlush = false;
+static unsigned long long s_flushEpoch = 0;       // bumped whenever a non-empty queue is executed
 
 // device-side op, in tile coordinates
 struct TileOp {
@@ -787,6 +788,7 @@ static char* s_devDesc = nullptr; static size_t s_devDescBytes = 0;
 static int flush_queue() {
     if (s_queue.empty() || s_inFlush) return 0;
     s_inFlush = true;
+    s_flushEpoch++;
     std::vector<QOp> ops; ops.swap(s_queue);
     qb_state q = s_qstate; s_qvalid = false;
     const int n = q.logNumAmpsPerNode;
@@ -912,6 +914,20 @@ static int flush_queue() {
 }
 
 int qb_flush_internal() { return flush_queue(); }
+
+// what the deferred queue of this state still holds: number of gates, and every suffix qubit any of them involves
+// (targets, controls, diagonal / Z sites).  The sharding layer uses it to run a half-shard swap AHEAD of the queued
+// gates when they commute with it (no queued gate touches the swapped suffix qubit), instead of flushing the queue.
+extern "C" int qb_queue_info(const qb_state* q, unsigned long long* touchedSuffixMask, unsigned long long* flushEpoch) {
+    unsigned long long mask = 0; int len = 0;
+    if (q && s_qvalid && s_qstate.amps == q->amps) {
+        len = (int)s_queue.size();
+        for (const QOp& o : s_queue) mask |= nonDiagTargets(o) | diagQubits(o);
+    }
+    if (touchedSuffixMask) *touchedSuffixMask = mask;
+    if (flushEpoch) *flushEpoch = s_flushEpoch;
+    return len;
+}
 
 // ------------------------------------------------------------------------------------------
 // enqueue API used by the per-gate entry points

@@ -80,6 +80,8 @@ def run(args, rank, world, local_rank, n, n_local, config, dist):
         gates()
     barrier()
     launches0 = capi.lib().qb_launch_count()
+    import ctypes as _C
+    _nx = _C.c_ulonglong(); capi.lib().qb_p2p_stats(_C.byref(_nx), None); exch0 = _nx.value
     sampler = bench.ClockSampler(local_rank)
     if rank == 0:
         sampler.start()
@@ -93,6 +95,7 @@ def run(args, rank, world, local_rank, n, n_local, config, dist):
     barrier()
     clocks = sampler.stop() if rank == 0 else None
     launches = capi.lib().qb_launch_count() - launches0
+    capi.lib().qb_p2p_stats(_C.byref(_nx), None); timed_exchanges = _nx.value - exch0
     ms = torch.tensor([e0.elapsed_time(e1)], dtype=torch.float64, device=dev)
     dist.all_reduce(ms, op=dist.ReduceOp.MAX)
     ms_per_step = ms.item() / args.steps
@@ -109,14 +112,22 @@ def run(args, rank, world, local_rank, n, n_local, config, dist):
     dist.all_reduce(dt, op=dist.ReduceOp.MAX)
     e2e_s = dt.item() / args.steps
 
-    # per-gate breakdown (one extra untimed step): what the link and HBM achieve per gate class
+    # per-gate breakdown (one extra untimed step, gates issued and flushed one at a time): with lazy qubit relabelling
+    # a gate is "non-local" when it made the backend exchange half-shards (a target sat on a rank bit and was pulled
+    # into the shard) -- seen as a step of the backend's exchange counter while the gate was being issued
+    import ctypes as C
+    def exchanges():
+        a, b = C.c_ulonglong(), C.c_ulonglong()
+        capi.lib().qb_p2p_stats(C.byref(a), C.byref(b))
+        return a.value, b.value
     classes = {}
     stream = [(op, None) for op in bench.qft_stream(n)] + mats
-    # the QFT is issued gate by gate here so that each gate can be bracketed by events
     evs = []
     barrier()
+    x0 = exchanges()
     for op, m in stream:
         a, b = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        before = exchanges()
         a.record()
         if op[0] == "h":
             Q.applyHadamard(qureg, op[1])
@@ -128,10 +139,13 @@ def run(args, rank, world, local_rank, n, n_local, config, dist):
             apply_dense(op, m)
         capi.call("qb_flush")          # gate-by-gate here: this profile shows the unfused per-gate cost
         b.record()
-        evs.append((op, a, b))
+        after = exchanges()
+        evs.append((op, a, b, after[0] - before[0], after[1] - before[1]))
+    Q.syncQuESTEnv()
     barrier()
-    for op, a, b in evs:
-        cls, link = _classify(op, n_local)
+    x1 = exchanges()
+    for op, a, b, nx, link in evs:
+        cls = "relabelled_swap (no amplitude moves)" if op[0] == "swap" else (f"{'dense' if op[0] in ('h', 'm1', 'm2') else op[0]}_with_{nx}_swap_in" if nx else "local")
         c = classes.setdefault(cls, {"gates": 0, "ms": 0.0, "link_bytes_per_dir": 0, "hbm_algorithmic_bytes": 0})
         c["gates"] += 1
         c["ms"] += a.elapsed_time(b)
@@ -139,8 +153,9 @@ def run(args, rank, world, local_rank, n, n_local, config, dist):
         c["hbm_algorithmic_bytes"] += bench.algorithmic_bytes(op, 1 << n_local)
     for c in classes.values():
         c["link_gbs_per_dir"] = c["link_bytes_per_dir"] / (c["ms"] * 1e-3) / 1e9 if c["link_bytes_per_dir"] else None
-        c["hbm_algorithmic_gbs"] = c["hbm_algorithmic_bytes"] / (c["ms"] * 1e-3) / 1e9
+        c["hbm_algorithmic_gbs"] = c["hbm_algorithmic_bytes"] / (c["ms"] * 1e-3) / 1e9 if c["ms"] > 0 else None
         c["ms_per_gate"] = c["ms"] / c["gates"]
+    classes["exchanges_in_breakdown_step_incl_restore"] = x1[0] - x0[0]
     total_prob = Q.calcTotalProb(qureg)
     Q.destroyQureg(qureg)
 
@@ -152,8 +167,9 @@ def run(args, rank, world, local_rank, n, n_local, config, dist):
             pass
         peak_gbs = peaks.get("hbm_gbs", 6650.0)
         local = classes.get("local", {"hbm_algorithmic_gbs": 0.0, "hbm_algorithmic_bytes": 0, "gates": 1})
-        link_bytes = sum(c["link_bytes_per_dir"] for c in classes.values())
-        link_ms = sum(c["ms"] for k, c in classes.items() if k != "local")
+        nonlocal_cls = {k: c for k, c in classes.items() if isinstance(c, dict) and c["link_bytes_per_dir"]}
+        link_bytes = sum(c["link_bytes_per_dir"] for c in nonlocal_cls.values())
+        link_ms = sum(c["ms"] for c in nonlocal_cls.values())
         config.update({"unit_definition": "one gate applied to one 2^30-amplitude shard; a gate of the sharded circuit counts once per GPU",
                        "circuit_gates_per_s": num_gates / (ms_per_step * 1e-3),
                        "parallelism": f"state sharded over {world} GPUs on the top {int(math.log2(world))} qubits",
@@ -166,7 +182,8 @@ def run(args, rank, world, local_rank, n, n_local, config, dist):
                              "peak_source": "measured (MEASURED_PEAKS.json)" if "hbm_gbs" in peaks else "fallback (B200_PROFILING.md)",
                              "nvlink": {"achieved_gbs_per_dir_per_gpu": link_bytes / (link_ms * 1e-3) / 1e9 if link_ms else None,
                                         "peak_gbs_per_dir": 770.0, "peak_source": "B200_PROFILING.md measured peer copy (900 nominal)",
-                                        "non_local_gates": sum(c["gates"] for k, c in classes.items() if k != "local")}},
+                                        "non_local_gates": sum(c["gates"] for c in nonlocal_cls.values()),
+                                        "exchanges_per_timed_step": timed_exchanges / args.steps}},
                 "cpu_baseline": None,
                 "e2e": {"value": world * num_gates / e2e_s, "unit": "gates/s", "h2d_bytes_per_step": sum(64 if op[0] == "m1" else 256 for op in dense),
                         "d2h_bytes_per_step": 8, "ms_per_step": 1e3 * e2e_s, "result_prob_of_top_qubit_0": prob},

@@ -164,6 +164,24 @@ struct QubitMap {
 };
 
 static std::unordered_map<const void*, QubitMap> g_qubitMaps;
+
+// The backend defers fusable gates in a queue.  A gate that was resolved against this rank's bits before being queued
+// (a control or a diagonal / Z site on a rank bit) pins those bits until the queue runs: g_rankBitUse remembers, per
+// statevector, the backend's flush counter at the last such gate.  A swap-in may overtake the queue only if no
+// pinned gate is still in it.
+static std::unordered_map<const void*, unsigned long long> g_rankBitUse;
+
+static unsigned long long backendFlushEpoch() {
+    unsigned long long epoch = 0;
+    qb_queue_info(nullptr, nullptr, &epoch);
+    return epoch;
+}
+
+static void noteRankBitUse(Qureg q, const vector<int>& physQubits) {
+    if (!q.isDistributed || !q.isGpuAccelerated || q.isDensityMatrix) return;
+    for (int b : physQubits)
+        if (b >= q.logNumAmpsPerNode) { g_rankBitUse[q.gpuAmps] = backendFlushEpoch(); return; }
+}
 static bool g_inCanonicalise = false;
 
 static bool relabelEnabled() {
@@ -272,15 +290,32 @@ static bool pullTargetsIntoShard(Qureg qureg, QubitMap& m, vector<int>& targs, c
     for (size_t i = 0; i < targs.size(); i++) {
         if (targs[i] < nl) continue;
         qindex used = getBitMask(targs.data(), targs.size()) | getBitMask(const_cast<int*>(ctrls.data()), ctrls.size());
+
+        // may the exchange overtake the gates the backend still holds back?  Only over NVLink peer memory (the NCCL
+        // path flushes anyway), and only if none of them was resolved against a rank bit; it then prefers a victim that
+        // no queued gate touches, so that the queue survives the swap-in and keeps fusing across it
+        auto st = toState(qureg);
+        unsigned long long touched = 0, epoch = 0;
+        int queued = qb_queue_info(&st, &touched, &epoch);
+        auto pinned = g_rankBitUse.find(qureg.gpuAmps);
+        bool mayOvertake = qb_p2p_is_available() && (queued == 0 || pinned == g_rankBitUse.end() || pinned->second != epoch);
+
         int victim = -1;
-        for (int lo : {nl > 20 ? 16 : 0, 0}) {
-            for (int p = nl - 1; p >= lo; p--)
-                if (!getBit(used, p) && (victim < 0 || m.lastUse[m.logi[p]] < m.lastUse[m.logi[victim]]))
-                    victim = p;
-            if (victim >= 0) break;
+        for (int pass = 0; pass < 4 && victim < 0; pass++) {
+            bool wantUntouched = (pass < 2) && mayOvertake && queued > 0;
+            if (pass < 2 && !wantUntouched) continue;
+            int lo = (pass % 2 == 0 && nl > 20) ? 16 : 0;
+            for (int p = nl - 1; p >= lo; p--) {
+                if (getBit(used, p) || (wantUntouched && ((touched >> p) & 1))) continue;
+                if (victim < 0 || m.lastUse[m.logi[p]] < m.lastUse[m.logi[victim]]) victim = p;
+            }
         }
         if (victim < 0) return false;
-        swapPrefixWithSuffix(qureg, {}, {}, victim, targs[i]);
+
+        if (mayOvertake)
+            QB_CHECK( qb_p2p_swapHalvesDeferred(&st, victim, rankWithFlipped(qureg, {targs[i]})) );
+        else
+            swapPrefixWithSuffix(qureg, {}, {}, victim, targs[i]);
         int lt = m.logi[targs[i]], lv = m.logi[victim];
         m.logi[targs[i]] = lv; m.logi[victim] = lt;
         m.phys[lt] = victim; m.phys[lv] = targs[i];
@@ -297,12 +332,13 @@ static void relabelForDenseGate(Qureg qureg, vector<int>& ctrls, vector<int>& ta
         if (!mapEligible(qureg) || !qureg.isDistributed) return;
         bool prefixTarg = false;
         for (int t : targs) prefixTarg |= (t >= qureg.logNumAmpsPerNode);
-        if (!prefixTarg) return;
+        if (!prefixTarg) { noteRankBitUse(qureg, ctrls); return; }
         m = &getMap(qureg);
     }
     mapQubits(m, ctrls);
     mapQubits(m, targs);
     if (qureg.isDistributed) pullTargetsIntoShard(qureg, *m, targs, ctrls);
+    noteRankBitUse(qureg, ctrls);
 }
 
 static PauliStr mapPauliStr(QubitMap* m, PauliStr str) {
@@ -612,17 +648,11 @@ static void swapPrefixWithSuffix(Qureg qureg, vector<int> ctrls, vector<int> ctr
     int pairRank = rankWithFlipped(qureg, {prefixTarg});
     int suffixState = ! rankBit(qureg, prefixTarg);
 
-    // NVLink fast path: swap the two half-shards in place through peer memory, no packing and no buffer.
-    // The link is only efficient on long contiguous runs, and the run length of "all amps with suffix bit s = b"
-    // is 2^s amps; a low suffix qubit is therefore first swapped LOCALLY (an HBM-speed pass) with the top suffix
-    // qubit, whose half-shard is one contiguous block:  SWAP(p,s) = SWAP(s,h) SWAP(p,h) SWAP(s,h).
+    // NVLink fast path: swap the two half-shards in place through peer memory, no packing and no buffer; measured at
+    // ~585 GB/s per direction for every suffix position (profiles/r1_p2p_swap_probe.txt), so no relocation is needed
     if (ctrls.empty() && qureg.isGpuAccelerated && qureg.logNumAmpsPerNode >= 1 && qb_p2p_is_available()) {
         auto s = toState(qureg);
-        int top = (int) qureg.logNumAmpsPerNode - 1;
-        bool relocate = suffixTarg < 6 && suffixTarg != top;
-        if (relocate) accel_statevec_anyCtrlSwap_subA(qureg, {}, {}, suffixTarg, top);
-        QB_CHECK( qb_p2p_swapHalves(&s, relocate ? top : suffixTarg, pairRank) );
-        if (relocate) accel_statevec_anyCtrlSwap_subA(qureg, {}, {}, suffixTarg, top);
+        QB_CHECK( qb_p2p_swapHalves(&s, suffixTarg, pairRank) );
         return;
     }
 
@@ -818,7 +848,7 @@ template <class T>
 void localiser_statevec_anyCtrlAnyTargAnyMatr(Qureg qureg, vector<int> ctrls, vector<int> ctrlStates, vector<int> targs, T matr, bool conj) {
     if constexpr (util_isCompMatr<T>() || util_isCompMatr1<T>() || util_isCompMatr2<T>())
         relabelForDenseGate(qureg, ctrls, targs);
-    else { QubitMap* m = findMap(qureg); mapQubits(m, ctrls); mapQubits(m, targs); }
+    else { QubitMap* m = findMap(qureg); mapQubits(m, ctrls); mapQubits(m, targs); noteRankBitUse(qureg, ctrls); noteRankBitUse(qureg, targs); }
     if constexpr (util_isDiagMatr <T>()) phys_statevec_anyCtrlAnyTargDiagMatr(qureg,  ctrls, ctrlStates, targs, matr, 1, conj);
     if constexpr (util_isDiagMatr1<T>()) phys_statevec_anyCtrlOneTargDiagMatr(qureg,  ctrls, ctrlStates, targs[0], matr, conj);
     if constexpr (util_isDiagMatr2<T>()) phys_statevec_anyCtrlTwoTargDiagMatr(qureg,  ctrls, ctrlStates, targs[0], targs[1], matr, conj);
@@ -1448,6 +1478,7 @@ void localiser_statevec_anyCtrlSwap(Qureg qureg, vector<int> ctrls, vector<int> 
     }
     QubitMap* m = findMap(qureg);
     mapQubits(m, ctrls);
+    noteRankBitUse(qureg, ctrls);
     phys_statevec_anyCtrlSwap(qureg, ctrls, ctrlStates, mapQubit(m, targ1), mapQubit(m, targ2));
 }
 
@@ -1471,13 +1502,16 @@ void localiser_statevec_anyCtrlAnyTargDenseMatr(Qureg qureg, vector<int> ctrls, 
 void localiser_statevec_anyCtrlOneTargDiagMatr(Qureg qureg, vector<int> ctrls, vector<int> ctrlStates, int targ, DiagMatr1 matr, bool conj) {
     QubitMap* m = findMap(qureg);
     mapQubits(m, ctrls);
-    phys_statevec_anyCtrlOneTargDiagMatr(qureg, ctrls, ctrlStates, mapQubit(m, targ), matr, conj);
+    int t = mapQubit(m, targ);
+    noteRankBitUse(qureg, ctrls); noteRankBitUse(qureg, {t});
+    phys_statevec_anyCtrlOneTargDiagMatr(qureg, ctrls, ctrlStates, t, matr, conj);
 }
 
 void localiser_statevec_anyCtrlTwoTargDiagMatr(Qureg qureg, vector<int> ctrls, vector<int> ctrlStates, int targ1, int targ2, DiagMatr2 matr, bool conj) {
     QubitMap* m = findMap(qureg);
     mapQubits(m, ctrls);
     int t1 = mapQubit(m, targ1), t2 = mapQubit(m, targ2);
+    noteRankBitUse(qureg, ctrls); noteRankBitUse(qureg, {t1, t2});
     phys_statevec_anyCtrlTwoTargDiagMatr(qureg, ctrls, ctrlStates, t1, t2, matr, conj);
 }
 
@@ -1485,26 +1519,32 @@ void localiser_statevec_anyCtrlAnyTargDiagMatr(Qureg qureg, vector<int> ctrls, v
     QubitMap* m = findMap(qureg);
     mapQubits(m, ctrls);
     mapQubits(m, targs);
+    noteRankBitUse(qureg, ctrls); noteRankBitUse(qureg, targs);
     phys_statevec_anyCtrlAnyTargDiagMatr(qureg, ctrls, ctrlStates, targs, matr, exponent, conj);
 }
 
 void localiser_statevec_anyCtrlPauliTensor(Qureg qureg, vector<int> ctrls, vector<int> ctrlStates, PauliStr str, qcomp factor) {
     QubitMap* m = findMap(qureg);
     mapQubits(m, ctrls);
-    phys_statevec_anyCtrlPauliTensor(qureg, ctrls, ctrlStates, mapPauliStr(m, str), factor);
+    str = mapPauliStr(m, str);
+    noteRankBitUse(qureg, ctrls); noteRankBitUse(qureg, paulis_getInds(str));
+    phys_statevec_anyCtrlPauliTensor(qureg, ctrls, ctrlStates, str, factor);
 }
 
 void localiser_statevec_anyCtrlPhaseGadget(Qureg qureg, vector<int> ctrls, vector<int> ctrlStates, vector<int> targs, qreal phase) {
     QubitMap* m = findMap(qureg);
     mapQubits(m, ctrls);
     mapQubits(m, targs);
+    noteRankBitUse(qureg, ctrls); noteRankBitUse(qureg, targs);
     phys_statevec_anyCtrlPhaseGadget(qureg, ctrls, ctrlStates, targs, phase);
 }
 
 void localiser_statevec_anyCtrlPauliGadget(Qureg qureg, vector<int> ctrls, vector<int> ctrlStates, PauliStr str, qreal phase) {
     QubitMap* m = findMap(qureg);
     mapQubits(m, ctrls);
-    phys_statevec_anyCtrlPauliGadget(qureg, ctrls, ctrlStates, mapPauliStr(m, str), phase);
+    str = mapPauliStr(m, str);
+    noteRankBitUse(qureg, ctrls); noteRankBitUse(qureg, paulis_getInds(str));
+    phys_statevec_anyCtrlPauliGadget(qureg, ctrls, ctrlStates, str, phase);
 }
 
 qreal localiser_statevec_calcProbOfMultiQubitOutcome(Qureg qureg, vector<int> qubits, vector<int> outcomes) {
