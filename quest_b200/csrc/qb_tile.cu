@@ -54,7 +54,7 @@
 #define FUSE_MIN_LOG_AMPS 13          // smaller states use the direct kernels immediately
 #define STAR_SEGS 6                   // external-control tables: 6 segments x 6 bits of the global index
 
-enum { OP_DENSE1 = 0, OP_DENSE2, OP_PAULI, OP_SWAP, OP_DIAG, OP_PARITY, OP_STAR };
+enum { OP_DENSE1 = 0, OP_DENSE2, OP_PAULI, OP_SWAP, OP_DIAG, OP_PARITY, OP_STAR, OP_HSTAR };   // OP_HSTAR: Hadamard on t0 fused with the phase star centred on t0 (one QFT stage)
 enum { ROUND_REG = 0, ROUND_SMEM = 1 };
 
 // ------------------------------------------------------------------------------------------
@@ -99,7 +99,8 @@ enum { CODE_DENSE1 = 0,      // + 2 * l0 + hasInTileCtrl                (8)
        CODE_DENSE2 = 8,      // + 2 * pairIndex(l0, l1) + hasInTileCtrl (12)
        CODE_SWAP = 20,       // + pairIndex                             (6)
        CODE_PAULI = 26,      // + lmaskA - 1                            (15)
-       CODE_DIAG = 41, CODE_PARITY = 42, CODE_STAR = 43 };
+       CODE_DIAG = 41, CODE_PARITY = 42, CODE_STAR = 43,     // + l0 (centre among the round's bits), + 4 (centre elsewhere)
+       CODE_HSTAR = 48 };                                     // + l0 (the centre is a non-diagonal target: always a round bit)
 static inline int pair_index(int a, int b) { return a == 0 ? b - 1 : (a == 1 ? b + 1 : 5); }   // (0,1)(0,2)(0,3)(1,2)(1,3)(2,3) -> 0..5
 
 struct RoundHdr { int kind, opBase, numOps, pad; int b[RB]; };
@@ -228,6 +229,23 @@ __device__ __forceinline__ void reg_star_bit(cplx (&v)[RAMPS], cplx eb, const cp
     }
 }
 
+// one QFT stage on round bit L: Hadamard, then the phase star on the amplitudes whose bit L is set:
+//   v0' = (v0 + v1)/sqrt2,  v1' = (v0 - v1) * (eb * m[u1]) with eb already carrying the 1/sqrt2
+// 7 FP64 instructions per amplitude instead of 12 for the generic dense gate followed by the star
+template <int L>
+__device__ __forceinline__ void reg_hstar_bit(cplx (&v)[RAMPS], cplx ebs, const cplx* __restrict__ mu) {
+    const double s = 0.70710678118654752440;
+#pragma unroll
+    for (int u = 0; u < RAMPS; u++) {
+        if (u & (1 << L)) continue;
+        const int u1 = u | (1 << L);
+        const cplx a0 = v[u], a1 = v[u1];
+        const cplx f = cmul(ebs, mu[u1]);
+        v[u] = mk(s * (a0.x + a1.x), s * (a0.y + a1.y));
+        v[u1] = cmul(mk(a0.x - a1.x, a0.y - a1.y), f);
+    }
+}
+
 // ------------------------------------------------------------------------------------------
 // one register round on one tile.  The op loop is software-pipelined: while gate o runs on the FP64 pipe, the
 // dispatch quad and the first four matrix entries (or the phase-star table entries) of gate o+1 are already in flight,
@@ -318,6 +336,10 @@ __device__ __forceinline__ void reg_round(cplx* __restrict__ t, const RoundHdr& 
             case CODE_STAR + 1: reg_star_bit<1>(v, cmul(cmul(pa, pb), pc), op->m); break;
             case CODE_STAR + 2: reg_star_bit<2>(v, cmul(cmul(pa, pb), pc), op->m); break;
             case CODE_STAR + 3: reg_star_bit<3>(v, cmul(cmul(pa, pb), pc), op->m); break;
+            case CODE_HSTAR + 0: reg_hstar_bit<0>(v, cscale(0.70710678118654752440, cmul(cmul(pa, pb), pc)), op->m); break;
+            case CODE_HSTAR + 1: reg_hstar_bit<1>(v, cscale(0.70710678118654752440, cmul(cmul(pa, pb), pc)), op->m); break;
+            case CODE_HSTAR + 2: reg_hstar_bit<2>(v, cscale(0.70710678118654752440, cmul(cmul(pa, pb), pc)), op->m); break;
+            case CODE_HSTAR + 3: reg_hstar_bit<3>(v, cscale(0.70710678118654752440, cmul(cmul(pa, pb), pc)), op->m); break;
             default:            // CODE_STAR + 4: centre outside the round (a tile bit tested through `ok`, or external and set)
                 if (ok) reg_star(v, cmul(cmul(pa, pb), pc), op->m, ok);
                 break;
@@ -433,7 +455,7 @@ __global__ void __launch_bounds__(TILE_BLOCK, 1) k_tile_pass(cplx* __restrict__ 
         cplx* sf = starF[wg][(k >> 1) & 1];
 
         // per-tile factor of every phase star: the part of its phase that depends on bits OUTSIDE the tile
-        if (wtid < numOps && ops[wtid].kind == OP_STAR) {
+        if (wtid < numOps && (ops[wtid].kind == OP_STAR || ops[wtid].kind == OP_HSTAR)) {
             const StarTab& tb = tabs[ops[wtid].tab];
             cplx f = mk(1, 0);
 #pragma unroll
@@ -483,7 +505,7 @@ struct Pass { std::vector<int> opIdx; unsigned long long high = 0; };
 
 static inline unsigned long long nonDiagTargets(const QOp& o) {
     switch (o.kind) {
-    case OP_DENSE1: return 1ULL << o.t0;
+    case OP_DENSE1: case OP_HSTAR: return 1ULL << o.t0;
     case OP_DENSE2: case OP_SWAP: return (1ULL << o.t0) | (1ULL << o.t1);
     case OP_PAULI: return o.maskA;
     default: return 0;
@@ -499,6 +521,7 @@ static inline unsigned long long diagQubits(const QOp& o) {
     case OP_DIAG: d |= 1ULL << o.t0; if (o.numT > 1) d |= 1ULL << o.t1; break;
     case OP_PARITY: d |= o.maskA; break;
     case OP_STAR: d |= 1ULL << o.t0; for (auto& ce : o.star) d |= 1ULL << ce.first; break;
+    case OP_HSTAR: for (auto& ce : o.star) d |= 1ULL << ce.first; break;
     default: break;
     }
     return d;
@@ -677,7 +700,7 @@ static void emit_pass(const qb_state* q, const std::vector<QOp>& ops, const Pass
             t.p0 = pos[o.t0]; t.e0 = o.t0;
             if (o.numT > 1) { t.p1 = pos[o.t1]; t.e1 = o.t1; }
             break;
-        case OP_STAR: {
+        case OP_STAR: case OP_HSTAR: {
             t.p0 = pos[o.t0]; t.e0 = o.t0;
             StarTab tb;
             long double angIn[2][64] = {{0}}, angExt[STAR_SEGS][64] = {{0}};
@@ -693,7 +716,7 @@ static void emit_pass(const qb_state* q, const std::vector<QOp>& ops, const Pass
         } break;
         }
         unsigned need = 0;
-        if (o.kind == OP_DENSE1) need = 1u << t.p0;
+        if (o.kind == OP_DENSE1 || o.kind == OP_HSTAR) need = 1u << t.p0;
         else if (o.kind == OP_DENSE2 || o.kind == OP_SWAP) need = (1u << t.p0) | (1u << t.p1);
         else if (o.kind == OP_PAULI) need = t.inMaskA;
         needIn.push_back(need);
@@ -728,7 +751,7 @@ static void emit_pass(const qb_state* q, const std::vector<QOp>& ops, const Pass
                     std::swap(a, b);
                 }
                 t.l0 = a; t.l1 = b; t.code = CODE_DENSE2 + 2 * pair_index(a, b) + hasCtrl;
-            } else if (t.kind == OP_STAR) {
+            } else if (t.kind == OP_STAR || t.kind == OP_HSTAR) {
                 // per-register phase factors over the round's own bits; the tables keep every other bit
                 const QOp& qo = ops[order[o]];
                 t.l0 = (t.p0 >= 0) ? local[t.p0] : -1;
@@ -741,7 +764,8 @@ static void emit_pass(const qb_state* q, const std::vector<QOp>& ops, const Pass
                 for (int u = 0; u < RAMPS; u++) t.m[u] = mk((double)cosl(ang[u]), (double)sinl(ang[u]));
                 // centre among the round's bits: specialised body; centre elsewhere in the tile: a per-thread test
                 // carried by the in-tile control fields; centre outside the tile: the per-tile `active` test
-                if (t.l0 >= 0) t.code = CODE_STAR + t.l0;
+                if (t.kind == OP_HSTAR) t.code = CODE_HSTAR + t.l0;
+                else if (t.l0 >= 0) t.code = CODE_STAR + t.l0;
                 else { t.code = CODE_STAR + 4; if (t.p0 >= 0) { t.inCtrlMask = 1u << t.p0; t.inCtrlVals = 1u << t.p0; } }
             } else if (t.kind == OP_PAULI) {
                 t.lmaskA = t.lmaskB = 0;
@@ -824,6 +848,26 @@ static int flush_queue() {
         merged.push_back(ops[i++]);
     }
 
+    // 1b. a Hadamard immediately followed by the phase star centred on the same qubit is one QFT stage: fuse them
+    if (reorder) {
+        std::vector<QOp> fused;
+        auto isH = [](const QOp& o) {
+            if (o.kind != OP_DENSE1 || o.ctrlMask) return false;
+            const double s = 0.70710678118654752440, e = 1e-15;
+            return fabs(o.m[0].x - s) < e && fabs(o.m[1].x - s) < e && fabs(o.m[2].x - s) < e && fabs(o.m[3].x + s) < e &&
+                   o.m[0].y == 0 && o.m[1].y == 0 && o.m[2].y == 0 && o.m[3].y == 0;
+        };
+        for (size_t i = 0; i < merged.size(); i++) {
+            if (i + 1 < merged.size() && isH(merged[i]) && merged[i + 1].kind == OP_STAR && merged[i + 1].t0 == merged[i].t0) {
+                QOp hs = merged[i + 1];
+                hs.kind = OP_HSTAR; hs.algBytes += merged[i].algBytes;
+                fused.push_back(hs);
+                i++;
+            } else fused.push_back(merged[i]);
+        }
+        merged.swap(fused);
+    }
+
     // 2. grouping into passes: first-fit over the whole queue -- a pass takes every op (in program order) whose high
     //    non-diagonal targets still fit into its six free tile bits and that commutes with everything it overtakes
     std::vector<Pass> passes;
@@ -866,7 +910,7 @@ static int flush_queue() {
     Emitted E;
     std::vector<int> passKind, passArg;     // -1: direct op index, else index into E.hdrs
     for (auto& p : passes) {
-        bool direct = (p.high == ~0ULL) || (p.opIdx.size() == 1 && merged[p.opIdx[0]].kind != OP_STAR) || n < TILE_BITS;
+        bool direct = (p.high == ~0ULL) || (p.opIdx.size() == 1 && merged[p.opIdx[0]].kind != OP_STAR && merged[p.opIdx[0]].kind != OP_HSTAR) || n < TILE_BITS;
         if (direct) { for (int idx : p.opIdx) { passKind.push_back(-1); passArg.push_back(idx); } }
         else { passKind.push_back((int)E.hdrs.size()); passArg.push_back(0); emit_pass(&q, merged, p, E, reorder); }
     }
@@ -1045,6 +1089,12 @@ static int run_direct(const qb_state* q, const QOp& o) {
     }
     case OP_PAULI:
         return qb_pauli_raw(q, ctrls, cs, nc, o.maskA, o.maskB, m[0], m[1]);
+    case OP_HSTAR: {
+        const double s = 0.70710678118654752440;
+        qb_cplx h[4] = {{s, 0}, {s, 0}, {s, 0}, {-s, 0}};
+        int r = qb_statevec_anyCtrlOneTargDenseMatr_subA(q, ctrls, cs, 0, o.t0, h);
+        if (r) return r;
+    }   // fall through: then the star's controlled phases
     case OP_STAR: {
         // a star that did not end up in a tile pass: apply its controlled phases one by one
         for (auto& ce : o.star) {
