@@ -73,10 +73,32 @@ def dense_stream(n, seed=SEED, num=NUM_DENSE):
     return ops
 
 
+def cfg3_stream(n, seed=34008, num=100):
+    """BASELINE cfg 3: gates drawn uniformly from {H, Rx, CompMatr1, CNOT, CompMatr2}, targets uniform
+    over ALL n qubits, so ~log2(P)/n of the targets sit on rank bits"""
+    rng = np.random.default_rng(seed)
+    ops = []
+    for _ in range(num):
+        k = int(rng.integers(5))
+        if k == 0:
+            ops.append(("h", int(rng.integers(n))))
+        elif k == 1:
+            ops.append(("rx", int(rng.integers(n)), float(rng.uniform(0, 2 * math.pi))))
+        elif k == 2:
+            ops.append(("m1", int(rng.integers(n)), rand_unitary(rng, 2)))
+        elif k == 3:
+            c, t = (int(q) for q in rng.choice(n, size=2, replace=False))
+            ops.append(("cnot", c, t))
+        else:
+            a, b = (int(q) for q in rng.choice(n, size=2, replace=False))
+            ops.append(("m2", a, b, rand_unitary(rng, 4)))
+    return ops
+
+
 def algorithmic_bytes(op, local_amps):
     """a gate on N local amps with c controls reads+writes 2*B*N/2^c; SWAP counts as c=1."""
     full = 2 * AMP_BYTES * local_amps
-    return full // 2 if op[0] in ("cphase", "swap") else full
+    return full // 2 if op[0] in ("cphase", "swap", "cnot") else full
 
 
 # ------------------------------------------------------------------------------------------------
@@ -226,6 +248,7 @@ def main():
     ap.add_argument("--cpu-budget", type=float, default=25.0, help="seconds of CPU work per reference step")
     ap.add_argument("--no-cpu-baseline", action="store_true")
     ap.add_argument("--no-e2e", action="store_true")
+    ap.add_argument("--workload", default="cfg2", choices=["cfg2", "cfg3"], help="cfg3 (N>1 only): 100 random {H,Rx,CompMatr1,CNOT,CompMatr2} gates on initPlusState")
     args = ap.parse_args()
 
     rank = int(os.environ.get("RANK", "0"))
@@ -236,6 +259,10 @@ def main():
     config = {"workload": f"cfg2: {n}q fp64 statevector, applyFullQuantumFourierTransform + {NUM_DENSE} random dense 1/2-qubit gates",
               "qubits": n, "amps_per_gpu": 1 << n_local, "gates_per_step": len(qft_stream(n)) + NUM_DENSE, "seed": SEED,
               "l2_policy": "state (16 GiB per GPU) is far larger than L2; every gate streams it from HBM"}
+
+    if args.workload == "cfg3":
+        config.update({"workload": f"cfg3: {n}q fp64 statevector, initPlusState + 100 random gates from {{H, Rx, CompMatr1, CNOT, CompMatr2}}, targets uniform over all qubits",
+                       "gates_per_step": 100, "seed": 34008})
 
     if args.impl == "reference":
         if rank != 0:

@@ -341,6 +341,20 @@ static void relabelForDenseGate(Qureg qureg, vector<int>& ctrls, vector<int>& ta
     noteRankBitUse(qureg, ctrls);
 }
 
+static PauliStr mapPauliStr(QubitMap* m, PauliStr str);
+
+// Pauli tensors / gadgets: X and Y sites are non-diagonal targets -- those on rank bits are pulled into the shard (one
+// half-shard exchange, then they stay) instead of the reference's full-shard exchange per gate (localiser.cpp:1271-1316);
+// Z sites are diagonal and are only translated
+static void relabelForPauli(Qureg qureg, vector<int>& ctrls, PauliStr& str) {
+    auto [x, y, z] = paulis_getSeparateInds(str, qureg);
+    vector<int> xy = util_getConcatenated(x, y);
+    relabelForDenseGate(qureg, ctrls, xy);            // translates ctrls; creates the map on first need
+    QubitMap* m = findMap(qureg);
+    str = mapPauliStr(m, str);
+    noteRankBitUse(qureg, paulis_getInds(str));
+}
+
 static PauliStr mapPauliStr(QubitMap* m, PauliStr str) {
     if (!m) return str;
     vector<int> codes, inds;
@@ -1524,10 +1538,7 @@ void localiser_statevec_anyCtrlAnyTargDiagMatr(Qureg qureg, vector<int> ctrls, v
 }
 
 void localiser_statevec_anyCtrlPauliTensor(Qureg qureg, vector<int> ctrls, vector<int> ctrlStates, PauliStr str, qcomp factor) {
-    QubitMap* m = findMap(qureg);
-    mapQubits(m, ctrls);
-    str = mapPauliStr(m, str);
-    noteRankBitUse(qureg, ctrls); noteRankBitUse(qureg, paulis_getInds(str));
+    relabelForPauli(qureg, ctrls, str);
     phys_statevec_anyCtrlPauliTensor(qureg, ctrls, ctrlStates, str, factor);
 }
 
@@ -1540,10 +1551,7 @@ void localiser_statevec_anyCtrlPhaseGadget(Qureg qureg, vector<int> ctrls, vecto
 }
 
 void localiser_statevec_anyCtrlPauliGadget(Qureg qureg, vector<int> ctrls, vector<int> ctrlStates, PauliStr str, qreal phase) {
-    QubitMap* m = findMap(qureg);
-    mapQubits(m, ctrls);
-    str = mapPauliStr(m, str);
-    noteRankBitUse(qureg, ctrls); noteRankBitUse(qureg, paulis_getInds(str));
+    relabelForPauli(qureg, ctrls, str);
     phys_statevec_anyCtrlPauliGadget(qureg, ctrls, ctrlStates, str, phase);
 }
 
