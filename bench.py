@@ -6,16 +6,22 @@ controlled phase shifts + 15 SWAPs, api/operations.cpp:1934-1953) followed by 20
 2-qubit unitaries on uniformly random targets (seed 20302) = 680 gates per step.
 For N>1 GPUs the state has 30+log2(N) qubits sharded over the ranks (2^30 amplitudes per GPU, weak scaling).
 
-  value   gates/s with the state resident in HBM: the gate stream is issued through the C ABI
-          (include/quest_b200.h), timed with CUDA events on the library's stream.
-  e2e     the same metric through the reference-facing boundary: QuEST's public API on the drop-in
-          libQuEST.so (initZeroState, applyFullQuantumFourierTransform, applyCompMatr1/2, calcProbOfQubitOutcome)
-          from HOST buffers.  A statevector simulator's per-step host inputs are the gate operands (matrices,
-          targets), which travel host->device inside every call; the state itself is created on the device by
-          the reference's own API (createQureg/initZeroState, api/qureg.cpp:143-174) and never crosses PCIe.
-          The step's result (a probability) is read back device->host.
-  roofline   the dense-gate kernel family (200 launches per step, 2*16*2^30 algorithmic bytes each): algorithmic
-          bytes / CUDA-event time of that section, against MEASURED_PEAKS.json hbm_gbs.
+Both timings drive QuEST's public API on the drop-in libQuEST.so (the call a user makes; the reference-facing
+boundary), so the sharding shim, the deferred gate queue and the kernels are all on the measured path.
+
+  value   gates/s with the state resident in HBM, CUDA events on the backend's stream.  The timed region is
+          K x (QFT + 200 dense gates) and ENDS with syncQuESTEnv(): the backend defers work (fusable gates are queued,
+          uncontrolled SWAPs only relabel qubits), and syncQuESTEnv() is what guarantees nothing is left undone
+          (it restores the canonical qubit order and drains the stream).  N>1: the unit is one gate applied to one
+          2^30-amplitude shard, so value = N x circuit gates / step time (quest_b200/dist_bench.py).
+  e2e     the same metric end to end with HOST buffers: initZeroState, the circuit (every matrix travels host ->
+          device inside its call), calcProbOfQubitOutcome read back device -> host; host wall clock.  A statevector
+          simulator's state is created on the device by the reference's own API (createQureg/initZeroState,
+          api/qureg.cpp:143-174) and never crosses PCIe; its per-step host inputs are the gate operands.
+  roofline   the dense-gate section: algorithmic bytes of its 200 gates (2*16*2^30 each) / CUDA-event
+          time of the section, against MEASURED_PEAKS.json hbm_gbs; frac > 1 is the gain of fusing several gates into
+          one HBM pass; physical_frac is the traffic actually moved (one read + one write of the state per launch,
+          confirmed by ncu in profiles/) against the same peak.
   cpu_baseline / --impl reference: the UNMODIFIED reference CPU/OpenMP library (oracle/_ref/libQuEST.so) on the
           box's host cores, timed on a bounded stratified sample of the same 680-gate stream at the same size.
 """
@@ -206,37 +212,6 @@ def run_reference(n, steps, warmup, sample_size, budget_s):
 # ------------------------------------------------------------------------------------------------
 # the product arm
 # ------------------------------------------------------------------------------------------------
-def make_calls(stream, capi, sref):
-    """pre-marshal every gate of the stream into a zero-argument closure over the C ABI"""
-    lib = capi.lib()
-    empty = capi.ints([])
-    h = capi.cplx_array(np.array([[1, 1], [1, -1]]) / math.sqrt(2))
-    calls = []
-    for op in stream:
-        if op[0] == "h":
-            calls.append((lib.qb_statevec_anyCtrlOneTargDenseMatr_subA, (sref, empty, empty, 0, op[1], h)))
-        elif op[0] == "cphase":
-            calls.append((lib.qb_statevec_anyCtrlOneTargDiagMatr_sub,
-                          (sref, capi.ints([op[2]]), capi.ints([1]), 1, op[1], capi.cplx_array([1, np.exp(1j * op[3])]))))
-        elif op[0] == "swap":
-            calls.append((lib.qb_statevec_anyCtrlSwap_subA, (sref, empty, empty, 0, op[1], op[2])))
-        elif op[0] == "m1":
-            calls.append((lib.qb_statevec_anyCtrlOneTargDenseMatr_subA, (sref, empty, empty, 0, op[1], capi.cplx_array(op[2]))))
-        else:
-            calls.append((lib.qb_statevec_anyCtrlTwoTargDenseMatr_sub, (sref, empty, empty, 0, op[1], op[2], capi.cplx_array(op[3]))))
-    return calls
-
-
-def issue(calls, capi):
-    """hand the gates to the backend one call per gate (as the reference API does), then make it launch whatever it
-    deferred: the backend queues fusable gates and runs them as multi-gate passes (quest_b200/csrc/qb_tile.cu)"""
-    for fn, args in calls:
-        rc = fn(*args)
-        if rc:
-            capi.check(rc, fn.__name__)
-    capi.call("qb_flush")
-
-
 def main():
     ap = argparse.ArgumentParser()
     ap.add_argument("--gpus", type=int, default=1)
@@ -389,7 +364,11 @@ def main():
     physical = passes * 2 * AMP_BYTES * local_amps / (t_dense * 1e-3) / 1e9
     roofline = {"kernel": "dense 1/2-qubit gate section: k_tile_pass (fused multi-gate passes) + direct k_tuple kernels",
                 "bound": "hbm", "achieved": achieved, "peak": peak_gbs,
-                "unit": "GB/s", "frac": achieved / peak_gbs, "traffic": None, "peak_source": peak_src,
+                "unit": "GB/s", "frac": achieved / peak_gbs,
+                # dram__bytes_read.sum + dram__bytes_write.sum per k_tile_pass launch, ncu --set full of this command
+                # (profiles/r1_final_launches_and_ncu.md): one read + one write of the state, whatever the number of fused gates
+                "traffic": 34.30e9 if n_local == 30 else None, "traffic_source": "ncu --set full, profiles/r1_final_launches_and_ncu.md",
+                "peak_source": peak_src,
                 "launches_per_step": passes, "gates_per_launch": len(dense) / max(passes, 1),
                 "algorithmic_bytes_per_launch": bytes_dense / max(passes, 1), "avg_launch_ms": t_dense / max(passes, 1),
                 "physical_gbs_estimate": physical, "physical_frac": physical / peak_gbs,
