@@ -166,22 +166,24 @@ struct QubitMap {
 static std::unordered_map<const void*, QubitMap> g_qubitMaps;
 
 // The backend defers fusable gates in a queue.  A gate that was resolved against this rank's bits before being queued
-// (a control or a diagonal / Z site on a rank bit) pins those bits until the queue runs: g_rankBitUse remembers, per
-// statevector, the backend's flush counter at the last such gate.  A swap-in may overtake the queue only if no
-// pinned gate is still in it.
-static std::unordered_map<const void*, unsigned long long> g_rankBitUse;
-
-static unsigned long long backendFlushEpoch() {
-    unsigned long long epoch = 0;
-    qb_queue_info(nullptr, nullptr, &epoch);
-    return epoch;
-}
+// (a control or a diagonal / Z site on a rank bit -- such a gate may even be dropped on the ranks whose bit mismatches,
+// so the queues of different ranks then differ) pins the rank bits until the queue has certainly run.  The flag is set
+// for every such gate and cleared only right after a flush that EVERY rank performs at the same point of the program
+// (a flushing swap-in, restoring the canonical order), so all ranks always agree on it: every decision below that looks
+// at the backend's queue is taken only while the flag is clear, i.e. while all ranks hold identical queues.
+static std::unordered_map<const void*, bool> g_rankBitsPinned;
 
 static void noteRankBitUse(Qureg q, const vector<int>& physQubits) {
     if (!q.isDistributed || !q.isGpuAccelerated || q.isDensityMatrix) return;
     for (int b : physQubits)
-        if (b >= q.logNumAmpsPerNode) { g_rankBitUse[q.gpuAmps] = backendFlushEpoch(); return; }
+        if (b >= q.logNumAmpsPerNode) { g_rankBitsPinned[q.gpuAmps] = true; return; }
 }
+
+static bool rankBitsPinned(Qureg q) {
+    auto it = g_rankBitsPinned.find(q.gpuAmps);
+    return it != g_rankBitsPinned.end() && it->second;
+}
+
 static bool g_inCanonicalise = false;
 
 static bool relabelEnabled() {
@@ -260,8 +262,10 @@ static void qbmap_reset(Qureg q) {
     if (!g_qubitMaps.empty() && q.gpuAmps != nullptr) g_qubitMaps.erase(q.gpuAmps);
 }
 
+
 void qbmap_forget(const void* gpuAmps) {
     if (!g_qubitMaps.empty()) g_qubitMaps.erase(gpuAmps);
+    g_rankBitsPinned.erase(gpuAmps);
 }
 
 void qbmap_canonicaliseHolding(const void* gpuPtr) {
@@ -295,10 +299,9 @@ static bool pullTargetsIntoShard(Qureg qureg, QubitMap& m, vector<int>& targs, c
         // path flushes anyway), and only if none of them was resolved against a rank bit; it then prefers a victim that
         // no queued gate touches, so that the queue survives the swap-in and keeps fusing across it
         auto st = toState(qureg);
-        unsigned long long touched = 0, epoch = 0;
-        int queued = qb_queue_info(&st, &touched, &epoch);
-        auto pinned = g_rankBitUse.find(qureg.gpuAmps);
-        bool mayOvertake = qb_p2p_is_available() && (queued == 0 || pinned == g_rankBitUse.end() || pinned->second != epoch);
+        bool mayOvertake = qb_p2p_is_available() && !rankBitsPinned(qureg);
+        unsigned long long touched = 0;
+        int queued = mayOvertake ? qb_queue_info(&st, &touched, nullptr) : 0;      // only consulted while all ranks' queues agree
 
         int victim = -1;
         for (int pass = 0; pass < 4 && victim < 0; pass++) {
@@ -314,8 +317,10 @@ static bool pullTargetsIntoShard(Qureg qureg, QubitMap& m, vector<int>& targs, c
 
         if (mayOvertake)
             QB_CHECK( qb_p2p_swapHalvesDeferred(&st, victim, rankWithFlipped(qureg, {targs[i]})) );
-        else
-            swapPrefixWithSuffix(qureg, {}, {}, victim, targs[i]);
+        else {
+            swapPrefixWithSuffix(qureg, {}, {}, victim, targs[i]);      // flushes the queue on every rank
+            g_rankBitsPinned[qureg.gpuAmps] = false;
+        }
         int lt = m.logi[targs[i]], lv = m.logi[victim];
         m.logi[targs[i]] = lv; m.logi[victim] = lt;
         m.phys[lt] = victim; m.phys[lv] = targs[i];
