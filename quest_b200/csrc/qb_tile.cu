@@ -613,11 +613,47 @@ struct Emitted {
     std::vector<int> opBase, roundBase;
 };
 
-static void emit_pass(const qb_state* q, const std::vector<QOp>& ops, const Pass& pass, Emitted& E, bool reorder) {
-    const int n = q->logNumAmpsPerNode;
-    // tile bit set S: the low bits, the required high bits, then filler (lowest unused bits) up to TILE_BITS
+// tile bit set of a pass: the low bits, the required high bits, then filler (lowest unused bits) up to TILE_BITS
+static unsigned long long tile_bit_set(int n, const Pass& pass) {
     unsigned long long S = ((1ULL << TILE_LOW) - 1) | pass.high;
     for (int b = TILE_LOW; b < n && __builtin_popcountll(S) < TILE_BITS; b++) S |= 1ULL << b;
+    return S;
+}
+
+// rounds: first-fit again, now over the pass's ops -- a round takes every op whose non-diagonal targets still fit into
+// its RB register bits and that commutes with the ops it overtakes.  `order` lists the pass's ops round by round.
+static void order_rounds(const std::vector<QOp>& ops, const Pass& pass, unsigned long long S, bool reorder,
+                         std::vector<int>& order, std::vector<int>& roundLen, std::vector<int>& roundKind) {
+    std::vector<int> remaining = pass.opIdx;
+    while (!remaining.empty()) {
+        const QOp& first = ops[remaining[0]];
+        if (first.kind == OP_PAULI && __builtin_popcountll(first.maskA & S) > RB) {      // shared-memory round of its own
+            order.push_back(remaining[0]); roundLen.push_back(1); roundKind.push_back(ROUND_SMEM);
+            remaining.erase(remaining.begin());
+            continue;
+        }
+        std::vector<int> taken, rest;
+        unsigned long long bits = 0;
+        first_fit(ops, remaining, 1000000, [&](const QOp& o, bool) {
+            const unsigned long long nb = bits | (nonDiagTargets(o) & S);
+            if (__builtin_popcountll(nb) > RB) return false;
+            bits = nb; return true;
+        }, taken, rest);
+        if (!reorder) {
+            size_t keep = 0;
+            while (keep < taken.size() && taken[keep] == remaining[keep]) keep++;
+            taken.resize(keep);
+            rest.assign(remaining.begin() + keep, remaining.end());
+        }
+        for (int idx : taken) order.push_back(idx);
+        roundLen.push_back((int)taken.size()); roundKind.push_back(ROUND_REG);
+        remaining.swap(rest);
+    }
+}
+
+static void emit_pass(const qb_state* q, const std::vector<QOp>& ops, const Pass& pass, Emitted& E, bool reorder) {
+    const int n = q->logNumAmpsPerNode;
+    const unsigned long long S = tile_bit_set(n, pass);
     int pos[64]; int sbits[TILE_BITS]; int T = 0;
     for (int b = 0; b < 64; b++) pos[b] = -1;
     for (int b = 0; b < n; b++) if ((S >> b) & 1) { pos[b] = T; sbits[T++] = b; }
@@ -651,36 +687,8 @@ static void emit_pass(const qb_state* q, const std::vector<QOp>& ops, const Pass
     auto toIn = [&](unsigned long long gm) { unsigned v = 0; for (int p = 0; p < T; p++) if ((gm >> sbits[p]) & 1) v |= 1u << p; return v; };
     const size_t opStart = E.ops.size();
 
-    // rounds: first-fit again, now over the pass's ops -- a round takes every op whose non-diagonal targets still fit
-    // into its RB register bits and that commutes with the ops it overtakes.  `order` lists the pass's ops round by round.
     std::vector<int> order, roundLen, roundKind;
-    {
-        std::vector<int> remaining = pass.opIdx;
-        while (!remaining.empty()) {
-            const QOp& first = ops[remaining[0]];
-            if (first.kind == OP_PAULI && __builtin_popcount(toIn(first.maskA)) > RB) {      // shared-memory round of its own
-                order.push_back(remaining[0]); roundLen.push_back(1); roundKind.push_back(ROUND_SMEM);
-                remaining.erase(remaining.begin());
-                continue;
-            }
-            std::vector<int> taken, rest;
-            unsigned bits = 0;
-            first_fit(ops, remaining, 1000000, [&](const QOp& o, bool) {
-                const unsigned nb = bits | toIn(nonDiagTargets(o));
-                if (__builtin_popcount(nb) > RB) return false;
-                bits = nb; return true;
-            }, taken, rest);
-            if (!reorder) {
-                size_t keep = 0;
-                while (keep < taken.size() && taken[keep] == remaining[keep]) keep++;
-                taken.resize(keep);
-                rest.assign(remaining.begin() + keep, remaining.end());
-            }
-            for (int idx : taken) order.push_back(idx);
-            roundLen.push_back((int)taken.size()); roundKind.push_back(ROUND_REG);
-            remaining.swap(rest);
-        }
-    }
+    order_rounds(ops, pass, S, reorder, order, roundLen, roundKind);
 
     std::vector<unsigned> needIn;            // per op: tile-bit positions its non-diagonal targets occupy
     for (int idx : order) {
@@ -809,19 +817,12 @@ static bool is_cphase(const QOp& o) {
 // device scratch for pass descriptors (grown on demand)
 static char* s_devDesc = nullptr; static size_t s_devDescBytes = 0;
 
-static int flush_queue() {
-    if (s_queue.empty() || s_inFlush) return 0;
-    s_inFlush = true;
-    s_flushEpoch++;
-    std::vector<QOp> ops; ops.swap(s_queue);
-    qb_state q = s_qstate; s_qvalid = false;
-    const int n = q.logNumAmpsPerNode;
-    int rc = 0;
-    const bool reorder = g_qb.tileEngine != 2;
+// the planner proper (host only, no CUDA): gate absorption, phase-star merging, Hadamard+star fusion, pass grouping
+static void plan_passes(std::vector<QOp>& ops, bool reorder, std::vector<QOp>& merged, std::vector<Pass>& passes) {
     if (reorder) absorb_gates(ops);
 
     // 1. merge ladders of controlled phases that share a qubit into phase stars
-    std::vector<QOp> merged;
+    merged.clear();
     for (size_t i = 0; i < ops.size(); ) {
         if (is_cphase(ops[i])) {
             size_t j = i + 1;
@@ -870,7 +871,7 @@ static int flush_queue() {
 
     // 2. grouping into passes: first-fit over the whole queue -- a pass takes every op (in program order) whose high
     //    non-diagonal targets still fit into its six free tile bits and that commutes with everything it overtakes
-    std::vector<Pass> passes;
+    passes.clear();
     const int maxHigh = TILE_BITS - TILE_LOW;
     const unsigned long long lowMask = (1ULL << TILE_LOW) - 1;
     auto highNeed = [&](const QOp& o) {
@@ -905,6 +906,20 @@ static int flush_queue() {
         remaining.swap(rest);
         passes.push_back(cur);
     }
+
+}
+
+static int flush_queue() {
+    if (s_queue.empty() || s_inFlush) return 0;
+    s_inFlush = true;
+    s_flushEpoch++;
+    std::vector<QOp> ops; ops.swap(s_queue);
+    qb_state q = s_qstate; s_qvalid = false;
+    const int n = q.logNumAmpsPerNode;
+    int rc = 0;
+    const bool reorder = g_qb.tileEngine != 2;
+    std::vector<QOp> merged; std::vector<Pass> passes;
+    plan_passes(ops, reorder, merged, passes);
 
     // 3. emit: single-op passes use the direct kernels (already at the HBM roofline), multi-op passes the tile kernel
     Emitted E;
@@ -1107,4 +1122,145 @@ static int run_direct(const qb_state* q, const QOp& o) {
     }
     }
     return qb_set_error(-1, "tile engine: unknown op", __FILE__, __LINE__);
+}
+
+// ------------------------------------------------------------------------------------------
+// host-only self-test of the planner (no CUDA): a random gate list is applied to a small random state vector twice --
+// gate by gate in program order, and in the planner's order (after gate absorption, star merging, Hadamard+star
+// fusion, pass grouping and round ordering) -- with a plain host simulator.  Exercised by tests/test_abi_cpu.py.
+// ------------------------------------------------------------------------------------------
+#include <complex>
+#include <random>
+
+typedef std::complex<double> hc;
+static inline hc tohc(cplx c) { return hc(c.x, c.y); }
+
+static void host_apply(std::vector<hc>& a, const QOp& o) {
+    const unsigned long long N = a.size();
+    auto ok = [&](unsigned long long i) { return (i & o.ctrlMask) == o.ctrlVals; };
+    switch (o.kind) {
+    case OP_DENSE1: {
+        const unsigned long long t = 1ULL << o.t0;
+        for (unsigned long long i = 0; i < N; i++) if (!(i & t) && ok(i)) {
+            hc x = a[i], y = a[i | t];
+            a[i] = tohc(o.m[0]) * x + tohc(o.m[1]) * y; a[i | t] = tohc(o.m[2]) * x + tohc(o.m[3]) * y;
+        }
+    } break;
+    case OP_DENSE2: {
+        const unsigned long long t0 = 1ULL << o.t0, t1 = 1ULL << o.t1;
+        for (unsigned long long i = 0; i < N; i++) if (!(i & (t0 | t1)) && ok(i)) {
+            hc v[4] = {a[i], a[i | t0], a[i | t1], a[i | t0 | t1]}, w[4];
+            for (int r = 0; r < 4; r++) { w[r] = 0; for (int c = 0; c < 4; c++) w[r] += tohc(o.m[4 * r + c]) * v[c]; }
+            a[i] = w[0]; a[i | t0] = w[1]; a[i | t1] = w[2]; a[i | t0 | t1] = w[3];
+        }
+    } break;
+    case OP_SWAP: {
+        const unsigned long long t0 = 1ULL << o.t0, t1 = 1ULL << o.t1;
+        for (unsigned long long i = 0; i < N; i++) if ((i & t0) && !(i & t1) && ok(i)) std::swap(a[i], a[i ^ t0 ^ t1]);
+    } break;
+    case OP_DIAG:
+        for (unsigned long long i = 0; i < N; i++) if (ok(i)) {
+            int k = (int)((i >> o.t0) & 1);
+            if (o.numT > 1) k |= (int)((i >> o.t1) & 1) << 1;
+            a[i] *= tohc(o.m[k]);
+        }
+        break;
+    case OP_PARITY:
+        for (unsigned long long i = 0; i < N; i++) if (ok(i)) a[i] *= tohc(o.m[__builtin_parityll(i & o.maskA)]);
+        break;
+    case OP_PAULI: {
+        const int h = 63 - __builtin_clzll(o.maskA);
+        for (unsigned long long i = 0; i < N; i++) if (!((i >> h) & 1) && ok(i)) {
+            const unsigned long long w = i ^ o.maskA;
+            const double si = __builtin_parityll(i & o.maskB) ? -1.0 : 1.0, sw = __builtin_parityll(w & o.maskB) ? -1.0 : 1.0;
+            hc x = a[i], y = a[w];
+            a[i] = tohc(o.m[0]) * x + tohc(o.m[1]) * sw * y; a[w] = tohc(o.m[0]) * y + tohc(o.m[1]) * si * x;
+        }
+    } break;
+    case OP_HSTAR: {
+        const unsigned long long t = 1ULL << o.t0; const double s = 0.70710678118654752440;
+        for (unsigned long long i = 0; i < N; i++) if (!(i & t)) { hc x = a[i], y = a[i | t]; a[i] = s * (x + y); a[i | t] = s * (x - y); }
+    }   // fall through to the star
+    case OP_STAR:
+        for (unsigned long long i = 0; i < N; i++) if ((i >> o.t0) & 1) {
+            double ang = 0;
+            for (auto& ce : o.star) if ((i >> ce.first) & 1) ang += ce.second;
+            a[i] *= hc(cos(ang), sin(ang));
+        }
+        break;
+    }
+}
+
+extern "C" int qb_selftest_planner(int numQubits, int numOps, unsigned seed, int reorder, double* maxErr, int* numPasses, int* numRounds, int* numOpsPlanned) {
+    if (numQubits < 3 || numQubits > 20 || numOps < 1) return -1;
+    std::mt19937_64 rng(seed);
+    auto rnd = [&](int n) { return (int)(rng() % (unsigned long long)n); };
+    auto unif = [&]() { return (double)(rng() >> 11) * (1.0 / 9007199254740992.0); };
+    auto rc = [&]() { return mk(2 * unif() - 1, 2 * unif() - 1); };
+    const int n = numQubits;
+    qb_state q; memset(&q, 0, sizeof q); q.numAmpsPerNode = 1LL << n; q.logNumAmpsPerNode = n; q.numQubits = n;
+    auto pick = [&](int k, int* out) { for (int i = 0; i < k; ) { int c = rnd(n); bool dup = false; for (int j = 0; j < i; j++) dup |= out[j] == c; if (!dup) out[i++] = c; } };
+
+    std::vector<QOp> ops;
+    while ((int)ops.size() < numOps) {
+        const int kind = rnd(10), nc = (rnd(3) == 0) ? rnd(3) : 0;
+        int qs[8]; pick(std::min(n, nc + 4), qs);
+        QOp o = blank(OP_DENSE1, &q, nc);
+        for (int i = 0; i < nc; i++) { o.ctrlMask |= 1ULL << qs[i]; if (rnd(2)) o.ctrlVals |= 1ULL << qs[i]; }
+        const int* t = qs + nc;
+        if (kind < 3) { o.kind = OP_DENSE1; o.t0 = t[0]; for (int i = 0; i < 4; i++) o.m[i] = rc(); ops.push_back(o); }
+        else if (kind < 6) { o.kind = OP_DENSE2; o.numT = 2; o.t0 = t[0]; o.t1 = t[1]; for (int i = 0; i < 16; i++) o.m[i] = rc(); ops.push_back(o); }
+        else if (kind == 6) { o.kind = OP_SWAP; o.numT = 2; o.t0 = t[0]; o.t1 = t[1]; ops.push_back(o); }
+        else if (kind == 7) {
+            if (rnd(2)) { o.kind = OP_DIAG; o.numT = 1 + rnd(2); o.t0 = t[0]; o.t1 = t[1]; for (int i = 0; i < 4; i++) o.m[i] = rc(); }
+            else { o.kind = OP_PARITY; for (int i = 0; i < 1 + rnd(3); i++) o.maskA |= 1ULL << t[i]; o.m[0] = rc(); o.m[1] = rc(); }
+            ops.push_back(o);
+        } else if (kind == 8) {
+            o.kind = OP_PAULI;
+            const int k = 1 + rnd(std::min(4, n - nc));
+            for (int i = 0; i < k; i++) { int p = rnd(3); if (p != 2) o.maskA |= 1ULL << t[i]; if (p != 0) o.maskB |= 1ULL << t[i]; }
+            if (!o.maskA) o.maskA = 1ULL << t[0];
+            o.m[0] = rc(); o.m[1] = rc();
+            ops.push_back(o);
+        } else {
+            // a QFT stage: Hadamard (sometimes absent) + a ladder of controlled phases on the same qubit
+            const int centre = rnd(n); const double s = 0.70710678118654752440;
+            if (rnd(4)) { QOp h = blank(OP_DENSE1, &q, 0); h.t0 = centre; h.m[0] = h.m[1] = h.m[2] = mk(s, 0); h.m[3] = mk(-s, 0); ops.push_back(h); }
+            const int len = 1 + rnd(std::min(n - 1, 6));
+            int others[8]; int cnt = 0;
+            while (cnt < len) { int c = rnd(n); bool bad = c == centre; for (int j = 0; j < cnt; j++) bad |= others[j] == c; if (!bad) others[cnt++] = c; }
+            for (int i = 0; i < len; i++) {
+                QOp d = blank(OP_DIAG, &q, 1); const double th = 6.28 * unif();
+                const bool flip = rnd(2);
+                d.t0 = flip ? others[i] : centre; d.ctrlMask = d.ctrlVals = 1ULL << (flip ? centre : others[i]);
+                d.m[0] = mk(1, 0); d.m[1] = mk(cos(th), sin(th));
+                ops.push_back(d);
+            }
+        }
+    }
+
+    std::vector<hc> ref((size_t)1 << n), got;
+    for (auto& v : ref) v = hc(2 * unif() - 1, 2 * unif() - 1);
+    got = ref;
+    for (const QOp& o : ops) host_apply(ref, o);
+
+    std::vector<QOp> queue = ops, merged; std::vector<Pass> passes;
+    plan_passes(queue, reorder != 0, merged, passes);
+    int rounds = 0, planned = 0;
+    for (const Pass& p : passes) {
+        if (p.high == ~0ULL || n < TILE_BITS) { for (int idx : p.opIdx) { host_apply(got, merged[idx]); planned++; } continue; }
+        std::vector<int> order, roundLen, roundKind;
+        order_rounds(merged, p, tile_bit_set(n, p), reorder != 0, order, roundLen, roundKind);
+        if (order.size() != p.opIdx.size()) return -2;
+        for (int idx : order) { host_apply(got, merged[idx]); planned++; }
+        rounds += (int)roundLen.size();
+    }
+    if (planned != (int)merged.size()) return -3;
+    double err = 0, norm = 0;
+    for (size_t i = 0; i < ref.size(); i++) { err = std::max(err, std::abs(ref[i] - got[i])); norm = std::max(norm, std::abs(ref[i])); }
+    if (maxErr) *maxErr = norm > 0 ? err / norm : err;
+    if (numPasses) *numPasses = (int)passes.size();
+    if (numRounds) *numRounds = rounds;
+    if (numOpsPlanned) *numOpsPlanned = planned;
+    return 0;
 }

@@ -69,3 +69,23 @@ def test_compute_fails_loudly_without_gpu():
     assert rc != 0 and b"no CPU fallback" in lib.qb_error_string()
     status = C.c_int(0)
     assert lib.qb_alloc(1024, C.byref(status)) is None and status.value != 0
+
+
+@pytest.mark.parametrize("reorder", [1, 0], ids=["absorb+reorder", "program-order"])
+@pytest.mark.parametrize("n", [4, 9, 13, 16])
+def test_tile_planner_preserves_the_circuit(n, reorder):
+    """host logic of the tile engine (quest_b200/csrc/qb_tile.cu: gate absorption, phase-star merging, Hadamard+star
+    fusion, commuting first-fit grouping into passes and rounds): a random gate list applied in the planner's order to a
+    small host state must equal gate-by-gate application in program order.  No GPU involved."""
+    lib = capi.lib()
+    err, passes, rounds, planned = C.c_double(), C.c_int(), C.c_int(), C.c_int()
+    for seed in range(8):
+        num_ops = 200
+        rc = lib.qb_selftest_planner(n, num_ops, 7000 + seed, reorder, C.byref(err), C.byref(passes), C.byref(rounds), C.byref(planned))
+        assert rc == 0, f"planner self-test failed structurally (rc={rc})"
+        assert err.value <= 1e-12, f"n={n} seed={seed}: planned order changes the state by {err.value:.3e}"
+        assert planned.value <= num_ops + 8
+        if n >= 13:
+            assert passes.value < planned.value       # gates really are grouped
+        if n >= 13 and reorder:
+            assert planned.value < num_ops            # absorption / merging shortened the list
