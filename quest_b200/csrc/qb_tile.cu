@@ -50,7 +50,7 @@
 #define RAMPS (1 << RB)               // amplitudes per register block
 #define TILE_MAX_CHUNKS (1 << (TILE_BITS - TILE_LOW))
 #define MAX_OPS_PER_PASS 48
-#define QUEUE_MAX 512
+#define QUEUE_MAX 2048                 // deferred gates before a forced flush (cfg 2 issues 680 per step)
 #define FUSE_MIN_LOG_AMPS 13          // smaller states use the direct kernels immediately
 #define STAR_SEGS 6                   // external-control tables: 6 segments x 6 bits of the global index
 

@@ -291,7 +291,7 @@ def measurement_program(n, seed):
     return {"seeds": [int(seed), 7], "quregs": {"psi": {"n": n, "init": "zero"}}, "ops": ops, "dump": ["psi"]}
 
 
-def relabel_program(n, seed, num_ops=160):
+def relabel_program(n, seed, num_ops=160, reads=True):
     """Stress of the lazy qubit relabelling (quest_b200/shim/localiser_b200.cpp): uncontrolled SWAPs (pure relabelling)
     and dense gates on every qubit (on several GPUs: targets on rank bits, pulled into the shard and left there)
     interleaved with the relabelling-aware gates and reductions, and with operations that must first restore the
@@ -299,7 +299,7 @@ def relabel_program(n, seed, num_ops=160):
     rng = np.random.default_rng(seed)
     ops = []
     for _ in range(num_ops):
-        r = int(rng.integers(14))
+        r = int(rng.integers(14 if reads else 12))        # reads=False: gates only, so the backend's queue is never flushed by a read
         if r < 3:
             a, b = _pick(rng, n, 2)
             ops.append(["applySwap", "psi", a, b])

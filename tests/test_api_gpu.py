@@ -48,7 +48,8 @@ def test_live_calcs_and_channels():
 
 def test_live_lazy_qubit_relabelling():
     """SWAP relabelling + restoring the canonical order where an operation needs it (single GPU: no rank bits)"""
-    _live([P.relabel_program(6, 4201), P.relabel_program(14, 4202), P.relabel_program(17, 4203, num_ops=120)])
+    _live([P.relabel_program(6, 4201), P.relabel_program(14, 4202), P.relabel_program(17, 4203, num_ops=120),
+           P.relabel_program(15, 4204, num_ops=2600, reads=False)])
 
 
 def test_live_cfg1_20q():

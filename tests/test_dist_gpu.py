@@ -47,10 +47,10 @@ def test_lazy_qubit_relabelling_sharded(world, p2p):
     """dense gates on rank bits pull the qubit into the shard and leave it there; SWAPs only relabel; everything else
     restores the canonical order first -- all invisible through the API"""
     logp = world.bit_length() - 1
-    # the last program is long enough to overflow the backend's 512-gate queue while gates with rank-bit controls have
+    # the last program is long enough to overflow the backend's 2048-gate queue while gates with rank-bit controls have
     # been dropped on some ranks only (the ranks' queues then differ in length)
     _check([P.relabel_program(logp + 3, 6301), P.relabel_program(logp + 7, 6302), P.relabel_program(logp + 13, 6303, num_ops=120),
-            P.relabel_program(logp + 13, 6304, num_ops=900)],
+            P.relabel_program(logp + 13, 6304, num_ops=2600, reads=False)],
            world, env={"QUEST_B200_P2P": p2p})
 
 
