@@ -243,6 +243,9 @@ def main():
         if rank != 0:
             return 0
         ref = run_reference(n_local, args.steps, max(args.warmup, 1), args.cpu_sample, args.cpu_budget)
+        if world > 1 or args.gpus > 1:
+            config["reference_note"] = (f"the metric's unit is one gate applied to 2^{n_local} amplitudes; the CPU reference is timed on that unit "
+                                        f"({n_local}-qubit state, all host cores): it cannot hold the {n}-qubit sharded state")
         line = {"impl": "reference", "metric": "30q fp64 gates/s", "value": ref["value"], "unit": "gates/s", "n_gpus": args.gpus,
                 "steps": args.steps, "warmup": args.warmup, "ms_per_step": ref["ms_per_step"], "higher_is_better": True,
                 "scaling": "weak", "vs_baseline": None, "dtype": "f64", "data": "synthetic", "config": config,
