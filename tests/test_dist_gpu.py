@@ -56,6 +56,16 @@ def test_lazy_qubit_relabelling_sharded(world, p2p):
 
 @pytest.mark.skipif(not WORLDS, reason="needs >= 2 GPUs")
 @pytest.mark.parametrize("world", WORLDS)
+def test_eager_swap_in_and_back_sharded(world):
+    """QUEST_B200_RELABEL=0: the reference's own strategy (swap prefix targets in, apply, swap back; SWAPs move
+    amplitudes; 1-target dense gates on a rank bit through the fused exchange kernel) stays correct"""
+    logp = world.bit_length() - 1
+    _check([P.relabel_program(logp + 6, 6401), P.cfg1_program(logp + 8, 6402, 100), P.cfg2_program(logp + 13, 6403, 40)],
+           world, env={"QUEST_B200_RELABEL": "0"})
+
+
+@pytest.mark.skipif(not WORLDS, reason="needs >= 2 GPUs")
+@pytest.mark.parametrize("world", WORLDS)
 def test_calcs_measurement_sharded(world):
     logp = world.bit_length() - 1
     _check([P.calcs_program_sv(logp + 5, 6101), P.measurement_program(logp + 5, 6102), P.cfg5_program(logp + 6, 6103, num_terms=30),
