@@ -281,3 +281,94 @@ def dephasing(sh, ket, prob):
         qo.densmatr_oneQubitDephasing_subA(st, ket, prob)
     else:
         qo.densmatr_oneQubitDephasing_subB(st, ket, prob)
+
+
+# ------------------------------------------------------------------------------------------------
+# lazy qubit relabelling: the CPU model of the "LAZY QUBIT RELABELLING" layer of quest_b200/shim/localiser_b200.cpp
+# ------------------------------------------------------------------------------------------------
+class RelabelledShard:
+    """A Shard plus the permutation logical qubit -> index bit.  Uncontrolled swaps only edit the permutation; a dense or
+    Pauli-X/Y target found on a rank bit is pulled into the shard with ONE prefix<->suffix swap against the least-recently-
+    used free suffix qubit and stays there (the reference swaps in, applies, swaps back: localiser.cpp:997-1040);
+    `canonicalise` undoes the permutation with physical swaps.  Every rank runs the same calls, so the copies agree."""
+
+    def __init__(self, sh, num_qubits):
+        self.sh = sh
+        self.phys = list(range(num_qubits))
+        self.logi = list(range(num_qubits))
+        self.last_use = [0] * num_qubits
+        self.clock = 0
+        self.exchanges = 0
+
+    def _map(self, qubits):
+        out = []
+        for q in qubits:
+            self.clock += 1
+            self.last_use[q] = self.clock
+            out.append(self.phys[q])
+        return out
+
+    def _physical_swap(self, a, b):
+        if a == b:
+            return
+        if not (self.sh.is_suffix(a) and self.sh.is_suffix(b)):
+            self.exchanges += 1
+        swap(self.sh, [], [], min(a, b), max(a, b))
+        la, lb = self.logi[a], self.logi[b]
+        self.logi[a], self.logi[b] = lb, la
+        self.phys[la], self.phys[lb] = b, a
+
+    def _pull(self, targs, ctrls):
+        nl = self.sh.logN
+        for i, t in enumerate(targs):
+            if t < nl:
+                continue
+            used = set(targs) | set(ctrls)
+            free = [p for p in range(nl) if p not in used]
+            if not free:
+                return
+            victim = min(free, key=lambda p: (self.last_use[self.logi[p]], -p))      # least recently used; ties: highest bit
+            self._physical_swap(victim, t)
+            targs[i] = victim
+
+    def relabel_swap(self, a, b):
+        pa, pb = self.phys[a], self.phys[b]
+        self.phys[a], self.phys[b] = pb, pa
+        self.logi[pa], self.logi[pb] = b, a
+
+    def dense(self, ctrls, states, targs, m):
+        c, t = self._map(ctrls), self._map(targs)
+        self._pull(t, c)
+        if len(t) == 1:
+            dense1(self.sh, c, states, t[0], m)
+        else:
+            denseK(self.sh, c, states, t, m)
+
+    def swap(self, ctrls, states, t1, t2):
+        if not ctrls:
+            self.relabel_swap(t1, t2)
+            return
+        c = self._map(ctrls)
+        a, b = self._map([t1, t2])
+        swap(self.sh, c, states, min(a, b), max(a, b))
+
+    def diag1(self, ctrls, states, targ, elems):
+        c = self._map(ctrls)
+        diag1(self.sh, c, states, self._map([targ])[0], elems)
+
+    def pauli(self, ctrls, states, x, y, z, ampFac, pairAmpFac):
+        c = self._map(ctrls)
+        xy = self._map(list(x) + list(y))
+        self._pull(xy, c)
+        pauli(self.sh, c, states, xy[:len(x)], xy[len(x):], self._map(z), ampFac, pairAmpFac)
+
+    def phase_gadget(self, ctrls, states, targs, phase):
+        phase_gadget(self.sh, self._map(ctrls), states, self._map(targs), phase)
+
+    def prob_of_outcome(self, qubits, outcomes):
+        return prob_of_outcome(self.sh, self._map(qubits), outcomes)
+
+    def canonicalise(self):
+        for l in range(len(self.phys)):
+            if self.phys[l] != l:
+                self._physical_swap(self.phys[l], l)

@@ -151,3 +151,59 @@ def test_sharded_oracle_matches_single_process(world, n):
     assert res["err"] <= 1e-12, res
     assert res["derr"] <= 1e-12, res
     assert res["prob"] <= 1e-12 and res["tot"] <= 1e-12 and res["exp"] <= 1e-12, res
+
+
+def _relabel_worker(rank, world, port, n, seed, q):
+    os.environ.update(MASTER_ADDR="127.0.0.1", MASTER_PORT=str(port))
+    dist.init_process_group("gloo", rank=rank, world_size=world)
+    try:
+        logp = world.bit_length() - 1
+        rng = np.random.default_rng(seed)
+        psi = rand_state(rng, n)
+        N = (1 << n) // world
+        st = qo.State(psi[rank * N:(rank + 1) * N].copy(), n, 0, rank, logp, np.zeros(N, dtype=np.complex128))
+        rs = qd.RelabelledShard(qd.Shard(st, rank, world), n)
+        glob = qo.State(psi.copy(), n)
+        probs = []
+        for op in _sv_ops(n, seed + 1, 80):
+            k = op[0]
+            if k == "dense1": rs.dense(op[1], op[2], [op[3]], op[4])
+            elif k == "swap": rs.swap(op[1], op[2], op[3], op[4])
+            elif k == "denseK": rs.dense(op[1], op[2], list(op[3]), op[4])
+            elif k == "diag1": rs.diag1(op[1], op[2], op[3], op[4])
+            elif k == "pauli": rs.pauli(op[1], op[2], op[3], op[4], op[5], op[6], op[7])
+            elif k == "phase": rs.phase_gadget(op[1], op[2], op[3], op[4])
+            _apply_global(glob, op)
+            if rng.integers(6) == 0:        # a relabelling-aware read in the middle of the permuted state
+                qs = _pick(rng, n, 2)
+                probs.append(abs(rs.prob_of_outcome(qs, [1, 0]) - qo.statevec_calcProbOfMultiQubitOutcome_sub(glob, qs, [1, 0])))
+        permuted = rs.phys != list(range(n))
+        exchanges_before_restore = rs.exchanges
+        rs.canonicalise()
+        gathered = [torch.empty(2 * N, dtype=torch.float64) for _ in range(world)]
+        dist.all_gather(gathered, torch.from_numpy(st.amps.view(np.float64).copy()))
+        full = np.concatenate([g.numpy().view(np.complex128) for g in gathered])
+        err = float(np.linalg.norm(full - glob.amps) / np.linalg.norm(glob.amps))
+        if rank == 0:
+            q.put({"err": err, "prob": max(probs) if probs else 0.0, "permuted": permuted, "exchanges": exchanges_before_restore})
+    finally:
+        dist.destroy_process_group()
+
+
+@pytest.mark.parametrize("world,n", [(2, 6), (4, 7)])
+def test_lazy_relabelling_model_matches_single_process(world, n):
+    """the lazy qubit relabelling of the sharding shim (swap = permutation edit, prefix targets pulled into the shard and
+    left there, relabelling-aware reads, canonical order restored at the end), restated in oracle/quest_oracle_dist.py and
+    run on gloo ranks, against the single-process oracle"""
+    ctx = mp.get_context("spawn")
+    q = ctx.Queue()
+    port = 29900 + world * 10 + n
+    procs = [ctx.Process(target=_relabel_worker, args=(r, world, port, n, 2000 + n, q)) for r in range(world)]
+    for p in procs:
+        p.start()
+    for p in procs:
+        p.join(timeout=300)
+        assert p.exitcode == 0, "a distributed worker failed"
+    res = q.get(timeout=10)
+    assert res["err"] <= 1e-12 and res["prob"] <= 1e-12, res
+    assert res["permuted"] and res["exchanges"] > 0, "the test circuit never exercised the relabelling"
