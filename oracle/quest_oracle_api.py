@@ -203,6 +203,24 @@ class OracleMachine:
             return None
         if name == "applySwap":
             return self.op("applyMultiStateControlledSwap", [a[0], [], [], 0, a[1], a[2]])
+        if name == "applyDiagMatr1":
+            self._unitary(Q[a[0]], self._diag, [], [], [a[1]], a[2], conj); return None
+        if name == "applyPhaseGadget":
+            self.applyPhaseGadget(Q[a[0]], [], [], a[1], a[3]); return None
+        if name == "applyTwoQubitPhaseShift":
+            # api/operations.cpp:1596-1614: a (numTargets-1)-controlled diag{1, e^{i angle}} on targets[0], controls targets[1:]
+            d = np.array([1, np.exp(1j * a[3])])
+            self._unitary(Q[a[0]], self._diag, [a[2]], [1], [a[1]], d, conj); return None
+        if name == "applyFullQuantumFourierTransform":
+            # api/operations.cpp:1934-1964: per qubit (top down) Hadamard + ladder of controlled phases, then the swaps
+            st = Q[a[0]]; n = st.numQubits
+            for t in range(n - 1, -1, -1):
+                self.op("applyHadamard", [a[0], t])
+                for m in range(t):
+                    self.op("applyTwoQubitPhaseShift", [a[0], t, t - m - 1, np.pi / (1 << (m + 1))])
+            for t in range(n // 2):
+                self.op("applySwap", [a[0], t, n - 1 - t])
+            return None
         if name == "setQuregToSuperposition":
             qo.statevec_setQuregToSuperposition_sub(a[0], Q[a[1]], a[2], Q[a[3]], a[4], Q[a[5]]); return None
         if name == "applyMultiQubitProjector":

@@ -21,10 +21,14 @@ FIXTURES = {
     "dense_big.pkl": [P.big_dense_program(8, 501, 6), P.big_dense_program(7, 503, 4), P.big_dense_program(6, 504, 5, nc=0)],
     "configs_small.pkl": [P.cfg1_program(10, num_gates=60), P.cfg2_program(9, num_gates=40), P.cfg4_program(5, layers=2),
                           P.cfg5_program(8, num_terms=12), P.measurement_program(7, 77)],
+    "relabel_sv.pkl": [P.relabel_program(6, 601), P.relabel_program(8, 602, num_ops=120), P.relabel_program(7, 603, num_ops=200, reads=False)],
 }
 
 if __name__ == "__main__":
+    only = set(sys.argv[1:])          # optional: regenerate just the named fixtures
     for fname, progs in FIXTURES.items():
+        if only and fname not in only:
+            continue
         outs = run_programs("ref", progs)
         path = os.path.join(ROOT, "tests", "golden", fname)
         pickle.dump({"programs": progs, "outputs": outs}, open(path, "wb"), protocol=4)

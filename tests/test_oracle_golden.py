@@ -13,7 +13,7 @@ from oracle import quest_oracle as qo
 from oracle.quest_oracle_api import run_program
 from tests import helpers as H
 
-FIXTURES = ["gates_sv.pkl", "gates_dm.pkl", "calcs_sv.pkl", "channels_dm.pkl", "dense_big.pkl"]
+FIXTURES = ["gates_sv.pkl", "gates_dm.pkl", "calcs_sv.pkl", "channels_dm.pkl", "dense_big.pkl", "relabel_sv.pkl"]
 
 
 @pytest.mark.parametrize("fname", FIXTURES)
@@ -27,7 +27,7 @@ def test_oracle_reproduces_reference(fname):
 def test_oracle_configs_small():
     """the BASELINE.json configurations at toy size: only the ops the interpreter restates are replayed."""
     fx = H.load_golden("configs_small.pkl")
-    for k in (0,):          # cfg1 uses H / CNOT / RotateX / CompMatr1 only
+    for k in (0, 1):        # cfg1: H / CNOT / RotateX / CompMatr1; cfg2: the QFT (H + controlled-phase ladders + swaps) + dense gates
         got = run_program(fx["programs"][k])
         H.assert_outputs_match(got, fx["outputs"][k], label=f"cfg[{k}]")
 
