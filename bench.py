@@ -166,7 +166,7 @@ import numpy as np
 import bench
 from quest_b200 import quest_api as qa
 n, steps, warmup, sample_size, budget = {n}, {steps}, {warmup}, {sample}, {budget}
-Q = qa.QuEST(qa.REF_LIB)
+Q = qa.QuEST(os.path.join({root!r}, "oracle", "_ref", "libQuEST.so"))      # the unmodified reference CPU build
 Q.initCustomQuESTEnv(0, 0, 1)
 q = Q.createCustomQureg(n, 0, 0, 0, 1)
 Q.initZeroState(q)

@@ -242,7 +242,6 @@ _SIGS = {
 
 REPO_ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
 B200_LIB = os.path.join(REPO_ROOT, "quest_b200", "lib", "libQuEST.so")
-REF_LIB = os.path.join(REPO_ROOT, "oracle", "_ref", "libQuEST.so")
 
 
 def _ints(seq):

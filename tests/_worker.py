@@ -16,7 +16,7 @@ def main():
     which, src, dst = sys.argv[1:4]
     progs = pickle.load(open(src, "rb"))
     if which == "ref":
-        Q = qa.QuEST(qa.REF_LIB)
+        Q = qa.QuEST(os.path.join(qa.REPO_ROOT, "oracle", "_ref", "libQuEST.so"))      # the checker: test infrastructure only
         Q.initCustomQuESTEnv(0, 0, 1)            # reference: CPU + OpenMP, the parity oracle
     elif which == "b200dist":
         # one process per GPU (RANK / WORLD_SIZE / LOCAL_RANK from the launcher); every Qureg is sharded

@@ -23,7 +23,7 @@ sys.path.insert(0, {root!r})
 from quest_b200 import quest_api as qa
 from quest_b200.program import run_program
 prog = pickle.load(open({src!r}, "rb"))
-Q = qa.QuEST(qa.REF_LIB); Q.initCustomQuESTEnv(0, 0, 1)
+Q = qa.QuEST(os.path.join({root!r}, "oracle", "_ref", "libQuEST.so")); Q.initCustomQuESTEnv(0, 0, 1)
 t0 = time.perf_counter(); out = run_program(Q, prog); dt = time.perf_counter() - t0
 pickle.dump(dict(seconds=dt, results=out["results"]), open({dst!r}, "wb"))
 """
