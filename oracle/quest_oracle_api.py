@@ -16,6 +16,7 @@ tests/golden/ through this interpreter and compares with what the UNMODIFIED ref
 import numpy as np
 
 from . import quest_oracle as qo
+from .quest_rng import MT19937_64
 
 
 def _dec(m):
@@ -64,6 +65,7 @@ class OracleMachine:
     def __init__(self, prog):
         self.prog = prog
         self.q = {}
+        self.rng = MT19937_64(prog["seeds"]) if "seeds" in prog else None      # setSeeds (core/randomiser.cpp:59-82)
 
     # ---- helpers --------------------------------------------------------------------------------
     def _bra(self, st, qubits):
@@ -239,6 +241,38 @@ class OracleMachine:
                 prob = qo.statevec_calcProbOfMultiQubitOutcome_sub(st, qubits, outcomes)
                 qo.statevec_multiQubitProjector_sub(st, qubits, outcomes, prob)
             return prob
+        if name == "applyQubitMeasurement":
+            # api/operations.cpp:1796-1827: two reductions, one uniform draw from the host mt19937_64, projector with the
+            # probability of the sampled outcome.  Returns the outcome (an integer: compared bit-exactly).
+            st, t = Q[a[0]], a[1]
+            if self.rng is None:
+                raise NotImplementedError("applyQubitMeasurement needs the program's seeds (default seeds come from std::random_device)")
+            calc = qo.densmatr_calcProbOfMultiQubitOutcome_sub if st.isDensityMatrix else qo.statevec_calcProbOfMultiQubitOutcome_sub
+            probs = [calc(st, [t], [0]), calc(st, [t], [1])]
+            outcome = self.rng.single_qubit_outcome(probs[0])
+            proj = qo.densmatr_multiQubitProjector_sub if st.isDensityMatrix else qo.statevec_multiQubitProjector_sub
+            proj(st, [t], [outcome], probs[outcome])
+            return outcome
+        if name == "applyTrotterizedPauliStrSumGadget":
+            # api/operations.cpp:1133-1197 (orders 1 and 2; higher orders recurse through the same first-order sweep)
+            terms, angle, order, reps = a[1][1], a[2], a[3], a[4]
+            if angle == 0:
+                return None
+
+            def first_order(ang, reverse):
+                seq = reversed(terms) if reverse else terms
+                for chars, inds, coeff in seq:
+                    self.op("applyPauliGadget", [a[0], ("pauli", chars, inds), 2 * ang * complex(coeff).real])
+
+            for _ in range(reps):
+                ang = angle / reps
+                if order == 1:
+                    first_order(ang, False)
+                elif order == 2:
+                    first_order(ang / 2, False); first_order(ang / 2, True)
+                else:
+                    raise NotImplementedError("Trotter order > 2 is not restated")
+            return None
         # ---- channels ----
         if name == "mixDephasing":
             qo.densmatr_oneQubitDephasing_subA(Q[a[0]], a[1], a[2]); return None

@@ -24,12 +24,32 @@ def test_oracle_reproduces_reference(fname):
         H.assert_outputs_match(got, want, tol=H.TOL, label=f"{fname}[{k}]")
 
 
+def _measure_ops(prog):
+    return {i for i, op in enumerate(prog["ops"]) if op[0] == "applyQubitMeasurement"}
+
+
 def test_oracle_configs_small():
-    """the BASELINE.json configurations at toy size: only the ops the interpreter restates are replayed."""
+    """the BASELINE.json configurations at toy size: cfg1 (H / CNOT / RotateX / CompMatr1), cfg2 (QFT + dense gates), cfg4
+    (noisy density-matrix circuit), cfg5 (2nd-order Trotter + Pauli-sum expectation) and the measurement program, whose
+    OUTCOMES must be bit-exact: the oracle restates the host mt19937_64 stream too (oracle/quest_rng.py)."""
     fx = H.load_golden("configs_small.pkl")
-    for k in (0, 1):        # cfg1: H / CNOT / RotateX / CompMatr1; cfg2: the QFT (H + controlled-phase ladders + swaps) + dense gates
-        got = run_program(fx["programs"][k])
-        H.assert_outputs_match(got, fx["outputs"][k], label=f"cfg[{k}]")
+    for k, (prog, want) in enumerate(zip(fx["programs"], fx["outputs"])):
+        got = run_program(prog)
+        H.assert_outputs_match(got, want, label=f"cfg[{k}]", int_exact_ops=_measure_ops(prog))
+
+
+def test_measurement_rng_stream_against_live_reference():
+    """std::seed_seq + std::mt19937_64 + uniform_real_distribution restated in oracle/quest_rng.py: many measurement outcomes
+    under several seed lists, against the live reference (skipped where oracle/_ref is absent)"""
+    if not os.path.exists(H.REF_LIB):
+        pytest.skip("oracle/_ref/libQuEST.so not built")
+    from tests import programs as P
+    progs = [P.measurement_program(9, 11), P.measurement_program(10, 123456789), P.measurement_program(8, 4242)]
+    progs[1]["seeds"] = [5, 6, 7, 8, 9]            # seed lists of other lengths exercise seed_seq's mixing
+    progs[2]["seeds"] = [4294967295]
+    wants = H.run_programs("ref", progs)
+    for k, (prog, want) in enumerate(zip(progs, wants)):
+        H.assert_outputs_match(run_program(prog), want, label=f"meas[{k}]", int_exact_ops=_measure_ops(prog))
 
 
 def test_oracle_against_live_reference():
