@@ -58,7 +58,8 @@ def test_oracle_against_live_reference():
         pytest.skip("oracle/_ref/libQuEST.so not built")
     from tests import programs as P
     progs = [P.gates_program(5, 9001), P.gates_program(3, 9002, dm=1, max_ctrls=1), P.calcs_program_sv(5, 9003),
-             P.channels_program_dm(3, 9004)]
+             P.channels_program_dm(3, 9004), P.big_dense_program(7, 9005, 4), P.cfg1_program(8, 9006, 40), P.cfg2_program(8, 9007, 30),
+             P.cfg4_program(4, 9008, layers=2), P.cfg5_program(7, 9009, num_terms=8), P.relabel_program(7, 9010)]
     wants = H.run_programs("ref", progs)
     for k, (prog, want) in enumerate(zip(progs, wants)):
         H.assert_outputs_match(run_program(prog), want, label=f"live[{k}]")
