@@ -205,6 +205,37 @@ def prob_of_outcome(sh, qubits, outcomes):
     return float(_reduce(prob).real)
 
 
+def projector(sh, qubits, outcomes, prob):
+    """localiser.cpp:2295-2314: ranks whose prefix bits contradict the outcome zero themselves; the others project on
+    their suffix qubits (or only renormalise when every projected qubit is a rank bit)"""
+    if not all(sh.is_suffix(q) or sh.rank_bit(q) == b for q, b in zip(qubits, outcomes)):
+        qo.statevec_initUniformState_sub(sh.st, 0)
+        return
+    qs = [(q, b) for q, b in zip(qubits, outcomes) if sh.is_suffix(q)]
+    if not qs:
+        sh.st.amps *= 1 / np.sqrt(prob)
+    else:
+        qo.statevec_multiQubitProjector_sub(sh.st, [q for q, _ in qs], [b for _, b in qs], prob)
+
+
+def densmatr_projector(sh, qubits, outcomes, prob):
+    """localiser.cpp:2317-2324: purely local; the kernel derives the global row/column from the rank"""
+    qo.densmatr_multiQubitProjector_sub(sh.st, list(qubits), list(outcomes), prob)
+
+
+def inner_product(shA, shB):
+    """localiser.cpp:2193-2215: local sums, then one all-reduce of a complex"""
+    return complex(_reduce(qo.statevec_calcInnerProduct_sub(shA.st, shB.st)))
+
+
+def two_qubit_dephasing(sh, ketA, ketB, prob):
+    """localiser.cpp:1439-1455: never communicates; the prefix variant reads the bra bits from the rank"""
+    if not sh.is_suffix(max(ketA, ketB) + sh.st.numQubits):
+        qo.densmatr_twoQubitDephasing_subB(sh.st, ketA, ketB, prob)
+    else:
+        qo.densmatr_twoQubitDephasing_subA(sh.st, ketA, ketB, prob)
+
+
 def total_prob(sh):
     return float(_reduce(qo.statevec_calcTotalProb_sub(sh.st)).real)
 

@@ -109,10 +109,18 @@ def _worker(rank, world, port, n, seed, q):
             x = [a for c, a in zip(chars, t) if c == "X"]; y = [a for c, a in zip(chars, t) if c == "Y"]; z = [a for c, a in zip(chars, t) if c == "Z"]
             want = qo.statevec_calcExpecPauliStr_subA(glob, x, y, z) if (x or y) else qo.statevec_calcExpecAnyTargZ_sub(glob, z)
             exps.append(abs(qd.expec_pauli(sh, x, y, z) - want))
+        # inner product with a second sharded register, then projectors on suffix and on rank-bit qubits
+        phi = rand_state(np.random.default_rng(seed + 3), n)
+        shB = qd.Shard(qo.State(phi[rank * N:(rank + 1) * N].copy(), n, 0, rank, logp, np.zeros(N, dtype=np.complex128)), rank, world)
+        ip_err = abs(qd.inner_product(sh, shB) - qo.statevec_calcInnerProduct_sub(glob, qo.State(phi.copy(), n)))
+        for qs in ([0], [n - 1], [1, n - 1]):
+            outs = [1] * len(qs)
+            pr = qo.statevec_calcProbOfMultiQubitOutcome_sub(glob, qs, outs)
+            qd.projector(sh, qs, outs, pr); qo.statevec_multiQubitProjector_sub(glob, qs, outs, pr)
         gathered = [torch.empty(2 * N, dtype=torch.float64) for _ in range(world)]
         dist.all_gather(gathered, torch.from_numpy(st.amps.view(np.float64).copy()))
         full = np.concatenate([g.numpy().view(np.complex128) for g in gathered])
-        err = float(np.linalg.norm(full - glob.amps) / np.linalg.norm(glob.amps))
+        err = float(np.linalg.norm(full - glob.amps) / np.linalg.norm(glob.amps)) + ip_err
 
         # density matrix channels with prefix bra qubits
         m = max(logp + 1, 3)
@@ -126,6 +134,9 @@ def _worker(rank, world, port, n, seed, q):
             qd.damping(dsh, ket, 0.2); qo.densmatr_oneQubitDamping_subA(dglob, ket, 0.2)
             qd.pauli_channel(dsh, ket, 0.1, 0.05, 0.2); qo.densmatr_oneQubitPauliChannel_subA(dglob, ket, 0.65, 0.1, 0.05, 0.2)
             qd.dephasing(dsh, ket, 0.15); qo.densmatr_oneQubitDephasing_subA(dglob, ket, 0.15)
+        qd.two_qubit_dephasing(dsh, 0, m - 1, 0.1); qo.densmatr_twoQubitDephasing_subA(dglob, 0, m - 1, 0.1)
+        pr = qo.densmatr_calcProbOfMultiQubitOutcome_sub(dglob, [m - 1], [0])
+        qd.densmatr_projector(dsh, [m - 1], [0], pr); qo.densmatr_multiQubitProjector_sub(dglob, [m - 1], [0], pr)
         gathered = [torch.empty(2 * Nd, dtype=torch.float64) for _ in range(world)]
         dist.all_gather(gathered, torch.from_numpy(dst.amps.view(np.float64).copy()))
         dfull = np.concatenate([g.numpy().view(np.complex128) for g in gathered])
