@@ -89,3 +89,29 @@ def test_tile_planner_preserves_the_circuit(n, reorder):
             assert passes.value < planned.value       # gates really are grouped
         if n >= 13 and reorder:
             assert planned.value < num_ops            # absorption / merging shortened the list
+
+
+def test_reference_example_links_against_the_dropin_library(tmp_path):
+    """the drop-in boundary at the API level: the reference's own tutorial (examples/tutorials/min_example.c) compiles
+    against QuEST's unchanged public headers, links against quest_b200/lib/libQuEST.so and runs.  Needs the reference tree
+    (build container only); without a GPU QuEST's auto-deployer places the Qureg on its own, untouched CPU backend."""
+    import shutil
+    import subprocess
+    ref = "/root/reference"
+    lib_dir = os.path.join(os.path.dirname(os.path.dirname(os.path.abspath(__file__))), "quest_b200", "lib")
+    if not os.path.isdir(ref) or not os.path.exists(os.path.join(lib_dir, "libQuEST.so")) or not shutil.which("gcc"):
+        pytest.skip("reference tree / drop-in library / gcc not available")
+    # what CMake generates from quest/include/quest.h.in for this build's options (Makefile: SHIM_DEFS)
+    (tmp_path / "quest.h").write_text(
+        "#ifndef QUEST_H\n#define QUEST_H\n#define FLOAT_PRECISION 2\n#define COMPILE_MPI 1\n#define COMPILE_OPENMP 1\n"
+        "#define COMPILE_CUDA 1\n#define COMPILE_CUQUANTUM 0\n" +
+        "".join(f'#include "quest/include/{h}.h"\n' for h in
+                ("version", "modes", "precision", "types", "calculations", "debug", "decoherence", "environment",
+                 "initialisations", "channels", "operations", "paulis", "qureg", "matrices", "wrappers")) + "#endif\n")
+    exe = tmp_path / "min_example"
+    subprocess.run(["gcc", "-std=c11", f"-I{ref}", f"-I{tmp_path}", f"{ref}/examples/tutorials/min_example.c", "-o", str(exe),
+                    f"-L{lib_dir}", "-lQuEST", f"-Wl,-rpath,{lib_dir}", "-lm"], check=True, capture_output=True, timeout=120)
+    env = {k: v for k, v in os.environ.items() if k not in ("RANK", "WORLD_SIZE", "LOCAL_RANK")}
+    out = subprocess.run([str(exe)], capture_output=True, text=True, timeout=300, env=env)
+    assert out.returncode == 0, out.stdout[-2000:] + out.stderr[-2000:]
+    assert "Total probability" in out.stdout and "isGpuCompiled...........1" in out.stdout
