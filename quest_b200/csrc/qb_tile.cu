@@ -140,8 +140,21 @@ template <int N> __device__ __forceinline__ void tma_wait_read() { asm volatile(
 template <int N> __device__ __forceinline__ void tma_wait_all() { asm volatile("cp.async.bulk.wait_group %0;" :: "n"(N) : "memory"); }
 __device__ __forceinline__ void fence_async_smem() { asm volatile("fence.proxy.async.shared::cta;" ::: "memory"); }
 
-__device__ __forceinline__ unsigned ins0(unsigned v, int p) { return ((v >> p) << (p + 1)) | (v & ((1u << p) - 1u)); }
-__device__ __forceinline__ cplx csel(bool c, cplx a, cplx b) { return mk(c ? a.x : b.x, c ? a.y : b.y); }
+// the gate bodies and the round driver below are compiled for the device (k_tile_pass) AND for the host, where the
+// CPU self-test qb_selftest_tile_emulation runs the very same code on the descriptors emit_pass produced
+#ifdef __CUDA_ARCH__
+#define QB_LDG(p) __ldg(p)
+#define QB_POPC(x) __popc(x)
+#define QB_CLZ(x) __clz(x)
+#else
+#define QB_LDG(p) (*(p))
+#define QB_POPC(x) __builtin_popcount(x)
+#define QB_CLZ(x) __builtin_clz(x)
+#endif
+#define QB_HD __host__ __device__ __forceinline__
+
+QB_HD unsigned ins0(unsigned v, int p) { return ((v >> p) << (p + 1)) | (v & ((1u << p) - 1u)); }
+QB_HD cplx csel(bool c, cplx a, cplx b) { return mk(c ? a.x : b.x, c ? a.y : b.y); }
 
 // ------------------------------------------------------------------------------------------
 // register-round gate bodies: v[u] is the amplitude whose round-bit pattern is u (bit k of u <-> round bit k);
@@ -149,7 +162,7 @@ __device__ __forceinline__ cplx csel(bool c, cplx a, cplx b) { return mk(c ? a.x
 // ------------------------------------------------------------------------------------------
 // CTRL = false: the gate has no in-tile controls, every amplitude is updated and no selects are emitted
 template <int K, bool CTRL>
-__device__ __forceinline__ void reg_dense1(cplx (&v)[RAMPS], cplx m00, cplx m01, cplx m10, cplx m11, unsigned ok) {
+QB_HD void reg_dense1(cplx (&v)[RAMPS], cplx m00, cplx m01, cplx m10, cplx m11, unsigned ok) {
 #pragma unroll
     for (int u = 0; u < RAMPS; u++) {
         if (u & (1 << K)) continue;
@@ -164,7 +177,7 @@ __device__ __forceinline__ void reg_dense1(cplx (&v)[RAMPS], cplx m00, cplx m01,
 // K0 < K1; matrix index bit 0 <-> K0, bit 1 <-> K1 (the host re-orders the matrix to make it so); the first matrix row
 // arrives in registers (prefetched while the previous gate ran), the other three are loaded while it is being used
 template <int K0, int K1, bool CTRL>
-__device__ __forceinline__ void reg_dense2(cplx (&v)[RAMPS], cplx r0, cplx r1, cplx r2, cplx r3, const cplx* __restrict__ mp, unsigned ok) {
+QB_HD void reg_dense2(cplx (&v)[RAMPS], cplx r0, cplx r1, cplx r2, cplx r3, const cplx* __restrict__ mp, unsigned ok) {
     cplx m[16];
     m[0] = r0; m[1] = r1; m[2] = r2; m[3] = r3;
 #pragma unroll
@@ -184,7 +197,7 @@ __device__ __forceinline__ void reg_dense2(cplx (&v)[RAMPS], cplx r0, cplx r1, c
 }
 
 template <int K0, int K1>
-__device__ __forceinline__ void reg_swap(cplx (&v)[RAMPS], unsigned ok) {
+QB_HD void reg_swap(cplx (&v)[RAMPS], unsigned ok) {
 #pragma unroll
     for (int u = 0; u < RAMPS; u++) {
         if (!(u & (1 << K0)) || (u & (1 << K1))) continue;       // u has K0 = 1, K1 = 0
@@ -197,14 +210,14 @@ __device__ __forceinline__ void reg_swap(cplx (&v)[RAMPS], unsigned ok) {
 
 // pairs (u, u ^ LXY); sign of amplitude u = (-1)^(parity of its Y/Z bits) = basePar ^ popc(u & lyz)
 template <int LXY>
-__device__ __forceinline__ void reg_pauli(cplx (&v)[RAMPS], unsigned lyz, int basePar, cplx af, cplx pf, unsigned ok) {
+QB_HD void reg_pauli(cplx (&v)[RAMPS], unsigned lyz, int basePar, cplx af, cplx pf, unsigned ok) {
     constexpr int H = (LXY & 8) ? 3 : (LXY & 4) ? 2 : (LXY & 2) ? 1 : 0;
 #pragma unroll
     for (int u = 0; u < RAMPS; u++) {
         if (u & (1 << H)) continue;
         const int w = u ^ LXY;
-        const double sA = 1.0 - 2.0 * ((__popc(u & lyz) + basePar) & 1);
-        const double sB = 1.0 - 2.0 * ((__popc(w & lyz) + basePar) & 1);
+        const double sA = 1.0 - 2.0 * ((QB_POPC(u & lyz) + basePar) & 1);
+        const double sB = 1.0 - 2.0 * ((QB_POPC(w & lyz) + basePar) & 1);
         cplx a = v[u], b = v[w];
         cplx nA = cfma(pf, cscale(sB, b), cmul(af, a)), nB = cfma(pf, cscale(sA, a), cmul(af, b));
         const bool c = (ok >> u) & 1;
@@ -213,7 +226,7 @@ __device__ __forceinline__ void reg_pauli(cplx (&v)[RAMPS], unsigned lyz, int ba
 }
 
 // phase star on the amplitudes selected by `on` (bit u): v[u] *= eb * m[u]
-__device__ __forceinline__ void reg_star(cplx (&v)[RAMPS], cplx eb, const cplx* __restrict__ mu, unsigned on) {
+QB_HD void reg_star(cplx (&v)[RAMPS], cplx eb, const cplx* __restrict__ mu, unsigned on) {
 #pragma unroll
     for (int u = 0; u < RAMPS; u++) {
         const cplx f = cmul(eb, mu[u]);
@@ -221,7 +234,7 @@ __device__ __forceinline__ void reg_star(cplx (&v)[RAMPS], cplx eb, const cplx* 
     }
 }
 template <int L>      // centre = round bit L: only the 8 amplitudes with that bit set are touched (no selects)
-__device__ __forceinline__ void reg_star_bit(cplx (&v)[RAMPS], cplx eb, const cplx* __restrict__ mu) {
+QB_HD void reg_star_bit(cplx (&v)[RAMPS], cplx eb, const cplx* __restrict__ mu) {
 #pragma unroll
     for (int u = 0; u < RAMPS; u++) {
         if (!(u & (1 << L))) continue;
@@ -233,7 +246,7 @@ __device__ __forceinline__ void reg_star_bit(cplx (&v)[RAMPS], cplx eb, const cp
 //   v0' = (v0 + v1)/sqrt2,  v1' = (v0 - v1) * (eb * m[u1]) with eb already carrying the 1/sqrt2
 // 7 FP64 instructions per amplitude instead of 12 for the generic dense gate followed by the star
 template <int L>
-__device__ __forceinline__ void reg_hstar_bit(cplx (&v)[RAMPS], cplx ebs, const cplx* __restrict__ mu) {
+QB_HD void reg_hstar_bit(cplx (&v)[RAMPS], cplx ebs, const cplx* __restrict__ mu) {
     const double s = 0.70710678118654752440;
 #pragma unroll
     for (int u = 0; u < RAMPS; u++) {
@@ -252,7 +265,7 @@ __device__ __forceinline__ void reg_hstar_bit(cplx (&v)[RAMPS], cplx ebs, const 
 // so the shared-memory latency of the descriptors never sits between two gates.
 // `active` (bit i <-> op i of the pass) holds the tile-uniform tests: external controls, external star centres.
 // ------------------------------------------------------------------------------------------
-__device__ __forceinline__ void reg_round(cplx* __restrict__ t, const RoundHdr& rd, const TileOp* __restrict__ ops, qindex base,
+QB_HD void reg_round(cplx* __restrict__ t, const RoundHdr& rd, const TileOp* __restrict__ ops, qindex base,
                                           unsigned long long active0, const StarTab* __restrict__ tabs, const cplx* __restrict__ starF, int wtid) {
   for (int it = 0; it < WG_ITERS; it++) {
     const int tid = wtid + it * WG_THREADS;
@@ -269,7 +282,7 @@ __device__ __forceinline__ void reg_round(cplx* __restrict__ t, const RoundHdr& 
     int4 d; cplx pa, pb, pc, pd;
 #define PREFETCH(q, D, A, B, C_, D_) do { \
         D = *reinterpret_cast<const int4*>(q); \
-        if (D.x >= CODE_STAR) { const StarTab& tb_ = tabs[(q)->tab]; A = __ldg(&tb_.in[0][jb & 63]); B = __ldg(&tb_.in[1][jb >> 6]); C_ = starF[(q) - ops]; D_ = C_; } \
+        if (D.x >= CODE_STAR) { const StarTab& tb_ = tabs[(q)->tab]; A = QB_LDG(&tb_.in[0][jb & 63]); B = QB_LDG(&tb_.in[1][jb >> 6]); C_ = starF[(q) - ops]; D_ = C_; } \
         else { A = (q)->m[0]; B = (q)->m[1]; C_ = (q)->m[2]; D_ = (q)->m[3]; } } while (0)
     PREFETCH(op, d, pa, pb, pc, pd);
 
@@ -303,7 +316,7 @@ __device__ __forceinline__ void reg_round(cplx* __restrict__ t, const RoundHdr& 
             case CODE_SWAP + 3: reg_swap<1, 2>(v, ok); break;
             case CODE_SWAP + 4: reg_swap<1, 3>(v, ok); break;
             case CODE_SWAP + 5: reg_swap<2, 3>(v, ok); break;
-#define PC(X) case CODE_PAULI + X - 1: reg_pauli<X>(v, op->lmaskB, (__popc(jb & op->inMaskB) + parity64((unsigned long long)base & op->extMaskB)) & 1, pa, pb, ok); break;
+#define PC(X) case CODE_PAULI + X - 1: reg_pauli<X>(v, op->lmaskB, (QB_POPC(jb & op->inMaskB) + parity64((unsigned long long)base & op->extMaskB)) & 1, pa, pb, ok); break;
             // sign bits of the Y/Z mask: those among the round's bits vary with u (lmaskB), the rest is fixed for this thread
             PC(1) PC(2) PC(3) PC(4) PC(5) PC(6) PC(7) PC(8) PC(9) PC(10) PC(11) PC(12) PC(13) PC(14) PC(15)
 #undef PC
@@ -325,7 +338,7 @@ __device__ __forceinline__ void reg_round(cplx* __restrict__ t, const RoundHdr& 
                 const int extPar = parity64((unsigned long long)base & op->extMaskB);
 #pragma unroll
                 for (int u = 0; u < RAMPS; u++) {
-                    const int par = (__popc((jb | OFF(u)) & inA) + extPar) & 1;
+                    const int par = (QB_POPC((jb | OFF(u)) & inA) + extPar) & 1;
                     v[u] = csel((ok >> u) & 1, cmul(v[u], par ? pb : pa), v[u]);
                 }
             } break;
@@ -356,18 +369,18 @@ __device__ __forceinline__ void reg_round(cplx* __restrict__ t, const RoundHdr& 
 
 // shared-memory fallback for the one gate shape that cannot live in a 4-bit register round:
 // Pauli strings with X/Y on more than four tile bits
-__device__ __forceinline__ void smem_pauli(cplx* __restrict__ t, const TileOp& op, qindex base, int wtid) {
+QB_HD void smem_pauli(cplx* __restrict__ t, const TileOp& op, qindex base, int wtid) {
     const unsigned cm = op.inCtrlMask, cv = op.inCtrlVals;
     const unsigned xy = op.inMaskA, yz = op.inMaskB;
-    const int h = 31 - __clz(xy);
+    const int h = 31 - QB_CLZ(xy);
     const int extPar = parity64((unsigned long long)base & op.extMaskB);
     const cplx af = op.m[0], pf = op.m[1];
     for (unsigned n = wtid; n < TILE_AMPS / 2; n += WG_THREADS) {
         unsigned jA = ins0(n, h);
         if ((jA & cm) != cv) continue;
         unsigned jB = jA ^ xy;
-        double sA = 1.0 - 2.0 * ((__popc(jA & yz) + extPar) & 1);
-        double sB = 1.0 - 2.0 * ((__popc(jB & yz) + extPar) & 1);
+        double sA = 1.0 - 2.0 * ((QB_POPC(jA & yz) + extPar) & 1);
+        double sB = 1.0 - 2.0 * ((QB_POPC(jB & yz) + extPar) & 1);
         cplx a = t[jA], b = t[jB];
         t[jA] = cfma(pf, cscale(sB, b), cmul(af, a));
         t[jB] = cfma(pf, cscale(sA, a), cmul(af, b));
@@ -1191,20 +1204,16 @@ static void host_apply(std::vector<hc>& a, const QOp& o) {
     }
 }
 
-extern "C" int qb_selftest_planner(int numQubits, int numOps, unsigned seed, int reorder, double* maxErr, int* numPasses, int* numRounds, int* numOpsPlanned) {
-    if (numQubits < 3 || numQubits > 20 || numOps < 1) return -1;
-    std::mt19937_64 rng(seed);
-    auto rnd = [&](int n) { return (int)(rng() % (unsigned long long)n); };
+// random gate list for the self-tests: every fusable kind, random controls, QFT-like stages
+static void selftest_random_ops(int n, int numOps, std::mt19937_64& rng, std::vector<QOp>& ops) {
+    auto rnd = [&](int k) { return (int)(rng() % (unsigned long long)k); };
     auto unif = [&]() { return (double)(rng() >> 11) * (1.0 / 9007199254740992.0); };
     auto rc = [&]() { return mk(2 * unif() - 1, 2 * unif() - 1); };
-    const int n = numQubits;
     qb_state q; memset(&q, 0, sizeof q); q.numAmpsPerNode = 1LL << n; q.logNumAmpsPerNode = n; q.numQubits = n;
     auto pick = [&](int k, int* out) { for (int i = 0; i < k; ) { int c = rnd(n); bool dup = false; for (int j = 0; j < i; j++) dup |= out[j] == c; if (!dup) out[i++] = c; } };
-
-    std::vector<QOp> ops;
     while ((int)ops.size() < numOps) {
         const int kind = rnd(10), nc = (rnd(3) == 0) ? rnd(3) : 0;
-        int qs[8]; pick(std::min(n, nc + 4), qs);
+        int qs[12]; pick(std::min(n, nc + 8), qs);
         QOp o = blank(OP_DENSE1, &q, nc);
         for (int i = 0; i < nc; i++) { o.ctrlMask |= 1ULL << qs[i]; if (rnd(2)) o.ctrlVals |= 1ULL << qs[i]; }
         const int* t = qs + nc;
@@ -1217,7 +1226,7 @@ extern "C" int qb_selftest_planner(int numQubits, int numOps, unsigned seed, int
             ops.push_back(o);
         } else if (kind == 8) {
             o.kind = OP_PAULI;
-            const int k = 1 + rnd(std::min(4, n - nc));
+            const int k = 1 + rnd(std::min(rnd(3) ? 4 : 8, n - nc));        // long strings: shared-memory rounds / direct passes
             for (int i = 0; i < k; i++) { int p = rnd(3); if (p != 2) o.maskA |= 1ULL << t[i]; if (p != 0) o.maskB |= 1ULL << t[i]; }
             if (!o.maskA) o.maskA = 1ULL << t[0];
             o.m[0] = rc(); o.m[1] = rc();
@@ -1238,6 +1247,15 @@ extern "C" int qb_selftest_planner(int numQubits, int numOps, unsigned seed, int
             }
         }
     }
+}
+
+extern "C" int qb_selftest_planner(int numQubits, int numOps, unsigned seed, int reorder, double* maxErr, int* numPasses, int* numRounds, int* numOpsPlanned) {
+    if (numQubits < 3 || numQubits > 20 || numOps < 1) return -1;
+    std::mt19937_64 rng(seed);
+    auto unif = [&]() { return (double)(rng() >> 11) * (1.0 / 9007199254740992.0); };
+    const int n = numQubits;
+    std::vector<QOp> ops;
+    selftest_random_ops(n, numOps, rng, ops);
 
     std::vector<hc> ref((size_t)1 << n), got;
     for (auto& v : ref) v = hc(2 * unif() - 1, 2 * unif() - 1);
@@ -1262,5 +1280,89 @@ extern "C" int qb_selftest_planner(int numQubits, int numOps, unsigned seed, int
     if (numPasses) *numPasses = (int)passes.size();
     if (numRounds) *numRounds = rounds;
     if (numOpsPlanned) *numOpsPlanned = planned;
+    return 0;
+}
+
+// ------------------------------------------------------------------------------------------
+// host emulation of k_tile_pass: the SAME round driver and gate bodies (reg_round, smem_pauli: compiled for host and
+// device) run tile by tile on the descriptors emit_pass produced -- tile base enumeration, chunk offsets, per-tile
+// control tests, per-tile star factors, rounds -- so that the whole host side of the tile engine (planner + emission)
+// and the device gate bodies are checked against plain gate-by-gate application without a GPU.
+// What stays GPU-only: the TMA / mbarrier pipeline that moves the tiles.
+// ------------------------------------------------------------------------------------------
+static void emulate_pass(std::vector<cplx>& amps, const Emitted& E, int hi) {
+    const PassHdr& hdr = E.hdrs[hi];
+    const RoundHdr* rounds = E.rounds.data() + E.roundBase[hi];
+    const TileOp* ops = E.ops.data() + E.opBase[hi];
+    const StarTab* tabs = E.tabs.data();
+    std::vector<cplx> t(TILE_AMPS);
+    cplx starF[MAX_OPS_PER_PASS];
+    for (qindex k = 0; k < hdr.numTiles; k++) {
+        const qindex base = hdr.tileIns(k);
+        for (int c = 0; c < hdr.numChunks; c++)                                   // what the copy warp's bulk loads do
+            for (int e = 0; e < hdr.chunkAmps; e++) t[(size_t)c * hdr.chunkAmps + e] = amps[base + hdr.chunkOff[c] + e];
+        unsigned long long active = 0;
+        for (int o = 0; o < hdr.numOps; o++) {
+            const TileOp& op = ops[o];
+            if (op.kind == OP_STAR || op.kind == OP_HSTAR) {
+                const StarTab& tb = tabs[op.tab];
+                cplx f = mk(1, 0);
+                for (int sg = 0; sg < STAR_SEGS; sg++) f = cmul(f, tb.ext[sg][(base >> (6 * sg)) & 63]);
+                starF[o] = f;
+            }
+            bool a = ((unsigned long long)base & op.extCtrlMask) == op.extCtrlVals;
+            if (op.kind == OP_STAR && op.p0 < 0) a = a && getBit(base, op.e0);
+            active |= (unsigned long long)a << o;
+        }
+        for (int r = 0; r < hdr.numRounds; r++) {
+            const RoundHdr& rd = rounds[r];
+            for (int wtid = 0; wtid < WG_THREADS; wtid++) {                       // the threads of a round touch disjoint amplitudes
+                if (rd.kind == ROUND_REG) reg_round(t.data(), rd, ops, base, active, tabs, starF, wtid);
+                else if ((active >> rd.opBase) & 1) smem_pauli(t.data(), ops[rd.opBase], base, wtid);
+            }
+        }
+        for (int c = 0; c < hdr.numChunks; c++)
+            for (int e = 0; e < hdr.chunkAmps; e++) amps[base + hdr.chunkOff[c] + e] = t[(size_t)c * hdr.chunkAmps + e];
+    }
+}
+
+extern "C" int qb_selftest_tile_emulation(int numQubits, int numOps, unsigned seed, int reorder, double* maxErr, int* numTilePasses, int* numDirectOps) {
+    if (numQubits < TILE_BITS || numQubits > 20 || numOps < 1) return -1;
+    std::mt19937_64 rng(seed);
+    auto unif = [&]() { return (double)(rng() >> 11) * (1.0 / 9007199254740992.0); };
+    const int n = numQubits;
+    std::vector<QOp> ops;
+    selftest_random_ops(n, numOps, rng, ops);
+    qb_state q; memset(&q, 0, sizeof q); q.numAmpsPerNode = 1LL << n; q.logNumAmpsPerNode = n; q.numQubits = n;
+
+    std::vector<hc> ref((size_t)1 << n);
+    for (auto& v : ref) v = hc(2 * unif() - 1, 2 * unif() - 1);
+    std::vector<cplx> state(ref.size());
+    for (size_t i = 0; i < ref.size(); i++) state[i] = mk(ref[i].real(), ref[i].imag());
+    for (const QOp& o : ops) host_apply(ref, o);
+
+    std::vector<QOp> queue = ops, merged; std::vector<Pass> passes;
+    plan_passes(queue, reorder != 0, merged, passes);
+    int tilePasses = 0, directOps = 0;
+    std::vector<hc> tmp;
+    for (const Pass& p : passes) {
+        const bool direct = (p.high == ~0ULL) || (p.opIdx.size() == 1 && merged[p.opIdx[0]].kind != OP_STAR && merged[p.opIdx[0]].kind != OP_HSTAR);
+        if (direct) {                                     // the product runs these through the direct kernels (GPU tests)
+            tmp.resize(state.size());
+            for (size_t i = 0; i < state.size(); i++) tmp[i] = tohc(state[i]);
+            for (int idx : p.opIdx) { host_apply(tmp, merged[idx]); directOps++; }
+            for (size_t i = 0; i < state.size(); i++) state[i] = mk(tmp[i].real(), tmp[i].imag());
+            continue;
+        }
+        Emitted E;
+        emit_pass(&q, merged, p, E, reorder != 0);
+        emulate_pass(state, E, 0);
+        tilePasses++;
+    }
+    double err = 0, norm = 0;
+    for (size_t i = 0; i < ref.size(); i++) { err = std::max(err, std::abs(ref[i] - tohc(state[i]))); norm = std::max(norm, std::abs(ref[i])); }
+    if (maxErr) *maxErr = norm > 0 ? err / norm : err;
+    if (numTilePasses) *numTilePasses = tilePasses;
+    if (numDirectOps) *numDirectOps = directOps;
     return 0;
 }

@@ -115,3 +115,21 @@ def test_reference_example_links_against_the_dropin_library(tmp_path):
     out = subprocess.run([str(exe)], capture_output=True, text=True, timeout=300, env=env)
     assert out.returncode == 0, out.stdout[-2000:] + out.stderr[-2000:]
     assert "Total probability" in out.stdout and "isGpuCompiled...........1" in out.stdout
+
+
+@pytest.mark.parametrize("reorder", [1, 0], ids=["absorb+reorder", "program-order"])
+@pytest.mark.parametrize("n", [12, 13, 15, 17])
+def test_tile_kernel_emulation_on_host(n, reorder):
+    """the tile engine end to end WITHOUT a GPU: planner -> emit_pass descriptors (tile enumeration, chunk offsets, round
+    bits, dispatch codes, phase-star tables) -> the kernel's own round driver and gate bodies, which are compiled for the
+    host as well as for the device (same source, quest_b200/csrc/qb_tile.cu) -> compared with plain gate-by-gate
+    application.  Only the TMA / mbarrier tile pipeline itself is left to the GPU tests."""
+    lib = capi.lib()
+    err, tile_passes, direct_ops = C.c_double(), C.c_int(), C.c_int()
+    total_tile_passes = 0
+    for seed in range(6):
+        rc = lib.qb_selftest_tile_emulation(n, 160, 8100 + seed, reorder, C.byref(err), C.byref(tile_passes), C.byref(direct_ops))
+        assert rc == 0
+        assert err.value <= 1e-12, f"n={n} seed={seed}: emulated tile passes differ from gate-by-gate application by {err.value:.3e}"
+        total_tile_passes += tile_passes.value
+    assert total_tile_passes > 0
