@@ -257,6 +257,12 @@ int qb_comm_end(void);                                              /* comm_end 
 int qb_comm_is_init(void);
 int qb_comm_rank(void);
 int qb_comm_num_ranks(void);
+/* transport of the NEXT communicator id made by qb_comm_get_unique_id: 0 = NCCL over NVLink (default; also taken from
+ * QUEST_B200_TRANSPORT=nccl|shm), 1 = shared host memory + CUDA IPC, for boxes with fewer GPUs than ranks (ranks share
+ * a device, as the reference allows with PERMIT_NODES_TO_SHARE_GPU, CMakeLists.txt:235-240, api/environment.cpp:110).
+ * The id carries the choice, so qb_comm_init on every rank follows rank 0. */
+int qb_comm_set_transport(int transport);
+int qb_comm_transport(void);                                        /* of the live communicator: 0 NCCL, 1 shared memory */
 int qb_comm_barrier(void);                                          /* comm_sync  comm_config.cpp:130 */
 /* send numAmps from dev `send` to pairRank while receiving numAmps into dev `recv` (comm_routines.cpp:209-232) */
 int qb_comm_exchange(const qb_cplx* devSend, qb_cplx* devRecv, qb_index numAmps, int pairRank);

@@ -8,17 +8,24 @@
 // Amplitude traffic goes GPU-to-GPU directly: device pointers are handed to ncclSend/ncclRecv on the
 // library's compute stream, so an exchange is ordered after the kernels that produced its input and
 // before the kernels that consume its output without any host synchronisation (the reference
-// cudaDeviceSynchronize()s before every exchange, comm_routines.cpp:390).  Large exchanges are split
-// into chunks so that the consumer kernel of chunk i can overlap the transfer of chunk i+1
-// (qb_comm_exchange_chunked, used by the localiser shim).
+// cudaDeviceSynchronize()s before every exchange, comm_routines.cpp:390).
+//
+// Second transport, for boxes with fewer GPUs than ranks (qb_comm_shm.cu): NCCL refuses two ranks on one device, so
+// when the communicator id was made by the shared-memory transport every entry point below routes to it instead --
+// same ABI, same semantics, host-synchronous.  It exists so that the sharding logic can be verified with 2/4/8 ranks
+// on a single GPU (the reference's CI shares GPUs between MPI ranks for the same reason, CMakeLists.txt:235-240).
 #include "qb_common.cuh"
+#include "qb_comm_shm.cuh"
 #include <nccl.h>
+#include <stdlib.h>
 #include <string.h>
 #include <vector>
 
 static ncclComm_t s_comm = nullptr;
 static int s_rank = 0, s_numRanks = 1;
 static bool s_init = false;
+static bool s_shm = false;                // this communicator runs over the shared-memory / CUDA-IPC transport
+static int s_wantTransport = -1;          // -1: from QUEST_B200_TRANSPORT (default nccl); 0: nccl; 1: shm
 static char* s_devScratch = nullptr;      // small device staging area for host-side collectives
 static char* s_hostScratch = nullptr;     // pinned
 static size_t s_scratchBytes = 0;
@@ -30,6 +37,14 @@ static int nccl_error(ncclResult_t r, const char* what, const char* file, int li
 }
 #define QB_NCCL(call) do { ncclResult_t r__ = (call); if (r__ != ncclSuccess) return nccl_error(r__, #call, __FILE__, __LINE__); } while (0)
 #define QB_COMM_READY() do { QB_READY(); QB_REQUIRE(s_init, "communicator not initialised (qb_comm_init)"); } while (0)
+// host-side collectives of the shared-memory transport also serve a rank that has no device (control-plane tests)
+#define QB_COMM_READY_HOST() do { if (!(s_shm && g_qb.device < 0)) QB_READY(); QB_REQUIRE(s_init, "communicator not initialised (qb_comm_init)"); } while (0)
+
+static bool want_shm() {
+    if (s_wantTransport >= 0) return s_wantTransport == 1;
+    const char* e = getenv("QUEST_B200_TRANSPORT");
+    return e && strcmp(e, "shm") == 0;
+}
 
 static int ensureScratch(size_t bytes) {
     if (bytes <= s_scratchBytes) return 0;
@@ -48,6 +63,7 @@ extern "C" {
 
 int qb_comm_get_unique_id(char id[QB_COMM_ID_BYTES]) {
     static_assert(sizeof(ncclUniqueId) <= QB_COMM_ID_BYTES, "ncclUniqueId larger than QB_COMM_ID_BYTES");
+    if (want_shm()) return shm_make_id(id, QB_COMM_ID_BYTES);
     ncclUniqueId uid;
     QB_NCCL(ncclGetUniqueId(&uid));
     memset(id, 0, QB_COMM_ID_BYTES);
@@ -61,7 +77,15 @@ int qb_comm_init(int rank, int numRanks, const char id[QB_COMM_ID_BYTES]) {
     QB_REQUIRE((numRanks & (numRanks - 1)) == 0, "qb_comm_init: number of ranks must be a power of two");
     // bind this process to "its" GPU before creating the communicator (gpu_config.cpp:332-353)
     int nd = qb_num_devices();
+    if (shm_is_id(id)) {
+        // ranks may share a device; a box without any device still gets the host-side collectives
+        if (nd > 0 && g_qb.device < 0) { int r = qb_bind_device(rank % nd); if (r) return r; }
+        int r = shm_init(rank, numRanks, id); if (r) return r;
+        s_shm = true; s_rank = rank; s_numRanks = numRanks; s_init = true;
+        return 0;
+    }
     QB_REQUIRE(nd > 0, "qb_comm_init: no CUDA device");
+    QB_REQUIRE(numRanks <= nd || numRanks == 1, "qb_comm_init: more ranks than GPUs needs the shared-memory transport (qb_comm_set_transport(1) / QUEST_B200_TRANSPORT=shm before the id is made)");
     if (g_qb.device < 0) { int r = qb_bind_device(rank % nd); if (r) return r; }
     ncclUniqueId uid;
     memcpy(&uid, id, sizeof uid);
@@ -72,8 +96,9 @@ int qb_comm_init(int rank, int numRanks, const char id[QB_COMM_ID_BYTES]) {
 
 int qb_comm_end(void) {
     if (!s_init) return 0;
-    cudaStreamSynchronize(g_qb.stream);
-    ncclCommDestroy(s_comm);
+    if (g_qb.device >= 0) cudaStreamSynchronize(g_qb.stream);
+    if (s_shm) shm_end(); else ncclCommDestroy(s_comm);
+    s_shm = false;
     s_comm = nullptr; s_init = false; s_rank = 0; s_numRanks = 1;
     return 0;
 }
@@ -81,10 +106,13 @@ int qb_comm_end(void) {
 int qb_comm_is_init(void) { return s_init ? 1 : 0; }
 int qb_comm_rank(void) { return s_rank; }
 int qb_comm_num_ranks(void) { return s_numRanks; }
+int qb_comm_set_transport(int transport) { s_wantTransport = (transport == 1) ? 1 : 0; return 0; }
+int qb_comm_transport(void) { return s_init && s_shm ? 1 : 0; }
 
 int qb_comm_allreduce_sum(double* hostValues, qb_index n) {
-    QB_COMM_READY();
+    QB_COMM_READY_HOST();
     if (n <= 0) return 0;
+    if (s_shm) return shm_allreduce_sum(hostValues, n);
     size_t bytes = sizeof(double) * (size_t)n;
     int r = ensureScratch(bytes); if (r) return r;
     memcpy(s_hostScratch, hostValues, bytes);
@@ -97,14 +125,15 @@ int qb_comm_allreduce_sum(double* hostValues, qb_index n) {
 }
 
 int qb_comm_barrier(void) {
-    QB_COMM_READY();
-    QB_CUDA(cudaDeviceSynchronize());
+    QB_COMM_READY_HOST();
+    if (g_qb.device >= 0) QB_CUDA(cudaDeviceSynchronize());
+    if (s_shm) return shm_barrier();
     double x = 0;
     return qb_comm_allreduce_sum(&x, 1);
 }
 
 int qb_comm_allreduce_and(int* hostFlag) {
-    QB_COMM_READY();
+    QB_COMM_READY_HOST();
     double v = *hostFlag ? 0.0 : 1.0;          // count the ranks on which the flag is false
     int r = qb_comm_allreduce_sum(&v, 1); if (r) return r;
     *hostFlag = (v == 0.0);
@@ -115,6 +144,7 @@ int qb_comm_exchange(const qb_cplx* devSend, qb_cplx* devRecv, qb_index numAmps,
     QB_COMM_READY();
     QB_REQUIRE(pairRank >= 0 && pairRank < s_numRanks && pairRank != s_rank, "exchange: bad pair rank");
     if (numAmps <= 0) return 0;
+    if (s_shm) return shm_exchange((const cplx*)devSend, (cplx*)devRecv, numAmps, pairRank);
     QB_NCCL(ncclGroupStart());
     QB_NCCL(ncclSend(devSend, (size_t)numAmps * 2, ncclDouble, pairRank, s_comm, g_qb.stream));
     QB_NCCL(ncclRecv(devRecv, (size_t)numAmps * 2, ncclDouble, pairRank, s_comm, g_qb.stream));
@@ -126,6 +156,7 @@ int qb_comm_send(const qb_cplx* devSend, qb_index numAmps, int pairRank) {
     QB_COMM_READY();
     QB_REQUIRE(pairRank >= 0 && pairRank < s_numRanks && pairRank != s_rank, "send: bad pair rank");
     if (numAmps <= 0) return 0;
+    if (s_shm) return shm_send((const cplx*)devSend, numAmps, pairRank);
     QB_NCCL(ncclSend(devSend, (size_t)numAmps * 2, ncclDouble, pairRank, s_comm, g_qb.stream));
     return 0;
 }
@@ -134,6 +165,7 @@ int qb_comm_recv(qb_cplx* devRecv, qb_index numAmps, int pairRank) {
     QB_COMM_READY();
     QB_REQUIRE(pairRank >= 0 && pairRank < s_numRanks && pairRank != s_rank, "recv: bad pair rank");
     if (numAmps <= 0) return 0;
+    if (s_shm) return shm_recv((cplx*)devRecv, numAmps, pairRank);
     QB_NCCL(ncclRecv(devRecv, (size_t)numAmps * 2, ncclDouble, pairRank, s_comm, g_qb.stream));
     return 0;
 }
@@ -141,13 +173,15 @@ int qb_comm_recv(qb_cplx* devRecv, qb_index numAmps, int pairRank) {
 int qb_comm_allgather(const qb_cplx* devSend, qb_cplx* devRecv, qb_index numAmpsPerRank) {
     QB_COMM_READY();
     if (numAmpsPerRank <= 0) return 0;
+    if (s_shm) return shm_allgather((const cplx*)devSend, (cplx*)devRecv, numAmpsPerRank);
     QB_NCCL(ncclAllGather(devSend, devRecv, (size_t)numAmpsPerRank * 2, ncclDouble, s_comm, g_qb.stream));
     return 0;
 }
 
 int qb_comm_broadcast_bytes(void* hostBuf, size_t numBytes, int root) {
-    QB_COMM_READY();
+    QB_COMM_READY_HOST();
     if (numBytes == 0) return 0;
+    if (s_shm) return shm_broadcast(hostBuf, numBytes, root);
     int r = ensureScratch(numBytes); if (r) return r;
     if (s_rank == root) memcpy(s_hostScratch, hostBuf, numBytes);
     QB_CUDA(cudaMemcpyAsync(s_devScratch, s_hostScratch, numBytes, cudaMemcpyHostToDevice, g_qb.stream));
@@ -159,8 +193,9 @@ int qb_comm_broadcast_bytes(void* hostBuf, size_t numBytes, int root) {
 }
 
 int qb_comm_gather_bytes(const void* hostSend, void* hostRecvOnRoot, size_t numBytesPerRank, int root) {
-    QB_COMM_READY();
+    QB_COMM_READY_HOST();
     if (numBytesPerRank == 0) return 0;
+    if (s_shm) return shm_allgather_host(hostSend, (s_rank == root) ? hostRecvOnRoot : nullptr, numBytesPerRank);
     size_t total = numBytesPerRank * (size_t)(s_numRanks + 1);
     int r = ensureScratch(total); if (r) return r;
     // layout: [own contribution][gathered numRanks contributions]
@@ -176,10 +211,11 @@ int qb_comm_gather_bytes(const void* hostSend, void* hostRecvOnRoot, size_t numB
 
 int qb_comm_sendrecv_host(const qb_cplx* hostSend, qb_cplx* hostRecv, qb_index numAmps, int sendRank, int recvRank) {
     // comm_sendAmpsToRoot (comm_routines.cpp:643-671): sendRank's host array -> recvRank's host array
-    QB_COMM_READY();
+    QB_COMM_READY_HOST();
     if (numAmps <= 0 || sendRank == recvRank) return 0;
     if (s_rank != sendRank && s_rank != recvRank) return 0;
     size_t bytes = sizeof(qb_cplx) * (size_t)numAmps;
+    if (s_shm) return s_rank == sendRank ? shm_send_host(hostSend, bytes, recvRank) : shm_recv_host(hostRecv, bytes, sendRank);
     int r = ensureScratch(bytes); if (r) return r;
     if (s_rank == sendRank) {
         memcpy(s_hostScratch, hostSend, bytes);
@@ -202,6 +238,7 @@ int qb_comm_sendrecv_host(const qb_cplx* hostSend, qb_cplx* hostRecv, qb_index n
 // ------------------------------------------------------------------------------------------
 int qb_comm_internal_allgather_host(const void* send, void* recvAll, size_t bytesPerRank) {
     QB_COMM_READY();
+    if (s_shm) return shm_allgather_host(send, recvAll, bytesPerRank);
     size_t total = bytesPerRank * (size_t)(s_numRanks + 1);
     int r = ensureScratch(total); if (r) return r;
     memcpy(s_hostScratch, send, bytesPerRank);
@@ -216,6 +253,7 @@ int qb_comm_internal_allgather_host(const void* send, void* recvAll, size_t byte
 
 int qb_comm_internal_sendrecv_host(const void* send, void* recv, size_t bytes, int pairRank) {
     QB_COMM_READY();
+    if (s_shm) return shm_sendrecv_host(send, recv, bytes, pairRank);
     int r = ensureScratch(2 * bytes); if (r) return r;
     memcpy(s_hostScratch, send, bytes);
     QB_CUDA(cudaMemcpyAsync(s_devScratch, s_hostScratch, bytes, cudaMemcpyHostToDevice, g_qb.stream));
@@ -234,6 +272,7 @@ int qb_comm_internal_sendrecv_host(const void* send, void* recv, size_t bytes, i
 int qb_comm_internal_sync_with(const int* ranks, int numRanks) {
     QB_COMM_READY();
     if (numRanks <= 0) return 0;
+    if (s_shm) { QB_CUDA(cudaStreamSynchronize(g_qb.stream)); return shm_sync_with(ranks, numRanks); }
     int r = ensureScratch(2 * (size_t)s_numRanks + 16); if (r) return r;
     QB_NCCL(ncclGroupStart());
     for (int i = 0; i < numRanks; i++) {
@@ -243,4 +282,12 @@ int qb_comm_internal_sync_with(const int* ranks, int numRanks) {
     QB_NCCL(ncclGroupEnd());
     QB_CUDA(cudaStreamSynchronize(g_qb.stream));
     return 0;
+}
+
+// host-side rendezvous of a pair when the ranks share a device (qb_p2p.cu: a spinning flag kernel of one process could
+// starve the partner's kernel of the same GPU; the host can simply wait for its own stream and meet the partner)
+bool qb_comm_internal_is_shm() { return s_init && s_shm; }
+int qb_comm_internal_pair_sync_host(int pairRank) {
+    QB_CUDA(cudaStreamSynchronize(g_qb.stream));
+    return shm_pair_sync(pairRank);
 }

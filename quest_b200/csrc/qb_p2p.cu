@@ -23,10 +23,12 @@
 int qb_comm_internal_allgather_host(const void* send, void* recvAll, size_t bytesPerRank);
 int qb_comm_internal_sendrecv_host(const void* send, void* recv, size_t bytes, int pairRank);
 int qb_comm_internal_sync_with(const int* ranks, int numRanks);
+bool qb_comm_internal_is_shm();
+int qb_comm_internal_pair_sync_host(int pairRank);
 
 #define QB_P2P_MAX_RANKS 64
 
-struct Alloc { size_t bytes; bool exported; };
+struct Alloc { size_t bytes; bool exported; unsigned long long seq; };      // seq: n-th allocation of this process (SPMD: the same on every rank)
 static std::map<uintptr_t, Alloc> s_allocs;                          // local allocations made by qb_alloc
 static std::map<std::pair<uintptr_t,int>, void*> s_peerBase;         // (local base, pair rank) -> mapped partner base
 
@@ -36,7 +38,8 @@ static unsigned long long* s_peerFlags[QB_P2P_MAX_RANKS] = {nullptr}; // mapped 
 static unsigned long long s_epoch[QB_P2P_MAX_RANKS] = {0};
 static unsigned long long s_numExchanges = 0, s_linkBytesPerDir = 0;    // statistics (qb_p2p_stats)
 
-void qb_p2p_note_alloc(void* base, size_t bytes) { s_allocs[(uintptr_t)base] = Alloc{bytes, false}; }
+static unsigned long long s_allocSeq = 0;
+void qb_p2p_note_alloc(void* base, size_t bytes) { s_allocs[(uintptr_t)base] = Alloc{bytes, false, ++s_allocSeq}; }
 
 // called by qb_free before cudaFree: unmap what we imported for this logical allocation, and -- if the memory
 // was exported -- make sure every importer has unmapped it before it is released (collective, like destroyQureg)
@@ -93,12 +96,13 @@ static int peer_pointer(const void* localPtr, int pairRank, void** peerPtr) {
     auto key = std::make_pair(base, pairRank);
     auto found = s_peerBase.find(key);
     if (found == s_peerBase.end()) {
-        struct Msg { cudaIpcMemHandle_t h; unsigned long long offset, bytes; } mine, theirs;
+        struct Msg { cudaIpcMemHandle_t h; unsigned long long offset, bytes, seq; } mine, theirs;
         memset(&mine, 0, sizeof mine);
         QB_CUDA(cudaIpcGetMemHandle(&mine.h, (void*)base));
-        mine.offset = offset; mine.bytes = it->second.bytes;
+        mine.offset = offset; mine.bytes = it->second.bytes; mine.seq = it->second.seq;
         int r = qb_comm_internal_sendrecv_host(&mine, &theirs, sizeof mine, pairRank); if (r) return r;
-        QB_REQUIRE(theirs.offset == offset && theirs.bytes == mine.bytes, "p2p: partner's allocation does not mirror this rank's");
+        // the partner must be talking about the SAME logical allocation (two Quregs of equal size would pass a size check)
+        QB_REQUIRE(theirs.offset == offset && theirs.bytes == mine.bytes && theirs.seq == mine.seq, "p2p: partner's allocation does not mirror this rank's");
         void* mapped = nullptr;
         QB_CUDA(cudaIpcOpenMemHandle(&mapped, theirs.h, cudaIpcMemLazyEnablePeerAccess));
         it->second.exported = true;
@@ -108,17 +112,37 @@ static int peer_pointer(const void* localPtr, int pairRank, void** peerPtr) {
     return 0;
 }
 
-__global__ void k_pair_barrier(unsigned long long* peerSlot, volatile unsigned long long* mySlot, unsigned long long epoch) {
+// The spin is bounded: if the partner never arrives (its process died, or the ranks diverged) the kernel traps after
+// `timeoutNs`, which poisons the context -- the next runtime call of this rank fails and is reported through
+// error_cudaCallFailed -- instead of leaving an unkillable spinning kernel behind.
+__global__ void k_pair_barrier(unsigned long long* peerSlot, volatile unsigned long long* mySlot, unsigned long long epoch, unsigned long long timeoutNs) {
     __threadfence_system();
     *(volatile unsigned long long*)peerSlot = epoch;        // "my stream has reached epoch"
     __threadfence_system();
-    while (*mySlot < epoch) { }
+    unsigned long long t0 = 0;
+    for (unsigned long long it = 0; *mySlot < epoch; it++) {
+        if ((it & 0xFFF) == 0xFFF) {
+            unsigned long long now;
+            asm volatile("mov.u64 %0, %globaltimer;" : "=l"(now));
+            if (t0 == 0) t0 = now;
+            else if (now - t0 > timeoutNs) { printf("quest_b200: pair barrier timed out waiting for the partner GPU (epoch %llu)\n", epoch); __trap(); }
+        }
+    }
     __threadfence_system();
 }
 
+static unsigned long long pair_timeout_ns() {
+    static unsigned long long ns = 0;
+    if (!ns) { const char* e = getenv("QUEST_B200_PAIR_TIMEOUT_S"); double s = e ? atof(e) : 120.0; if (s <= 0) s = 120.0; ns = (unsigned long long)(s * 1e9); }
+    return ns;
+}
+
 static int pair_barrier(int pairRank) {
+    // ranks sharing one device rendezvous on the host (qb_comm_shm.cu): a spinning kernel would only hold the GPU
+    // against the very kernel it is waiting for
+    if (qb_comm_internal_is_shm()) return qb_comm_internal_pair_sync_host(pairRank);
     unsigned long long epoch = ++s_epoch[pairRank];
-    k_pair_barrier<<<1, 1, 0, g_qb.stream>>>(s_peerFlags[pairRank] + qb_comm_rank(), s_myFlags + pairRank, epoch);
+    k_pair_barrier<<<1, 1, 0, g_qb.stream>>>(s_peerFlags[pairRank] + qb_comm_rank(), s_myFlags + pairRank, epoch, pair_timeout_ns());
     QB_LAUNCH_CHECK();
     return 0;
 }

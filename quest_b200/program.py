@@ -19,6 +19,7 @@ Special argument encodings (everything else is passed through as int/float/list-
   {"pauli": ["XZY", [q0,q1,q2]]} -> PauliStr;  {"paulisum": [["XZ", [q..], [re,im]], ...]} -> PauliStrSum
   {"c": [re, im]}       -> qcomp by value
   {"out_reals": k}      -> a qreal[k] output array (returned as the op's result)
+  {"amps": [[re,im]..]} -> a host qcomp array passed by pointer (setQuregAmps, setDensityQuregFlatAmps ...)
 Complex matrices are nested lists of [re, im] pairs (or anything np.asarray(...).view understands).
 """
 import ctypes as C
@@ -78,6 +79,8 @@ class _Interp:
                 strs = [Q.getPauliStr(t[0], t[1]) for t in v]
                 obj = Q.newPauliStrSum(strs, [complex(t[2][0], t[2][1]) for t in v])
                 self.cleanup.append(("destroyPauliStrSum", obj)); return obj
+            if k == "amps":
+                arr = np.ascontiguousarray(dec_mat(v), dtype=np.complex128); self.keep.append(arr); return arr.ctypes.data
             if k == "out_reals":
                 arr = (C.c_double * int(v))(); self.outarr = arr; return arr
             raise ValueError(f"unknown argument encoding {k}")

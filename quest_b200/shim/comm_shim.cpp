@@ -132,6 +132,11 @@ void comm_init() {
         if (numGpus > 0)
             QB_CHECK( qb_bind_device(local % numGpus) );
 
+        // fewer GPUs than ranks: ranks share devices, which NCCL refuses -- use the shared-memory / CUDA-IPC transport
+        // (the reference permits the same sharing for its tests: PERMIT_NODES_TO_SHARE_GPU, api/environment.cpp:110)
+        if (numGpus > 0 && s_numRanks > numGpus)
+            QB_CHECK( qb_comm_set_transport(1) );
+
         char id[QB_COMM_ID_BYTES];
         obtainUniqueId(id);
         QB_CHECK( qb_comm_init(s_rank, s_numRanks, id) );

@@ -148,6 +148,12 @@ bool gpu_areAnyNodesBoundToSameGpu() {
     if (!comm_isInit())
         return false;
 
+    // the shared-memory / CUDA-IPC transport exists precisely so that ranks may share a device (it is only chosen
+    // when there are fewer GPUs than ranks, or on request): the run-time twin of PERMIT_NODES_TO_SHARE_GPU
+    // (api/environment.cpp:110, core/validation.cpp:1365)
+    if (qb_comm_transport() == 1)
+        return false;
+
     // 16 raw UUID bytes are hex-encoded so that they survive the string gather intact
     char raw[16];
     QB_CHECK( qb_device_uuid(raw) );

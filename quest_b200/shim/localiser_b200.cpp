@@ -161,27 +161,54 @@ struct QubitMap {
     std::vector<int> logi;                    // logi[index bit] = logical qubit stored there
     std::vector<unsigned long long> lastUse;  // per logical qubit, for the swap-in victim choice
     unsigned long long clock = 0;
+    unsigned long long seq = 0;               // creation order: identical on every rank (maps are created at SPMD points)
 };
 
 static std::unordered_map<const void*, QubitMap> g_qubitMaps;
+static unsigned long long g_mapSeq = 0;
 
 // The backend defers fusable gates in a queue.  A gate that was resolved against this rank's bits before being queued
 // (a control or a diagonal / Z site on a rank bit -- such a gate may even be dropped on the ranks whose bit mismatches,
-// so the queues of different ranks then differ) pins the rank bits until the queue has certainly run.  The flag is set
-// for every such gate and cleared only right after a flush that EVERY rank performs at the same point of the program
-// (a flushing swap-in, restoring the canonical order), so all ranks always agree on it: every decision below that looks
-// at the backend's queue is taken only while the flag is clear, i.e. while all ranks hold identical queues.
+// so the queues of different ranks then differ) pins the rank bits until the queue has certainly run.
+//
+// Everything the relabelling layer decides from "what is still queued" must come out the same on every rank, or partner
+// GPUs would exchange different suffix bits.  The backend's own queue cannot be asked: ranks flush at different times
+// (setQuregAmps runs on the owning ranks only, a prefix/prefix swap only on the ranks whose two bits differ, a gate with
+// a rank-bit control is dropped on half of them).  So the shim keeps its own, rank-independent record, built from the
+// API-level arguments every rank sees identically:
+//   g_queuedBits[q]     suffix index bits involved in ANY gate handed to the backend since the last collective flush
+//                       (a superset of what any rank still holds queued),
+//   g_rankBitsPinned[q] some such gate involved a rank bit,
+// and both are cleared only at points where EVERY rank drains its queue at the same place in the program
+// (collectiveFlush: restoring the canonical order, syncQuESTEnv, a flushing swap-in).
 static std::unordered_map<const void*, bool> g_rankBitsPinned;
+static std::unordered_map<const void*, unsigned long long> g_queuedBits;
 
-static void noteRankBitUse(Qureg q, const vector<int>& physQubits) {
+static void noteGateQubits(Qureg q, const vector<int>& physQubits) {
     if (!q.isDistributed || !q.isGpuAccelerated || q.isDensityMatrix) return;
-    for (int b : physQubits)
-        if (b >= q.logNumAmpsPerNode) { g_rankBitsPinned[q.gpuAmps] = true; return; }
+    for (int b : physQubits) {
+        if (b >= q.logNumAmpsPerNode) g_rankBitsPinned[q.gpuAmps] = true;
+        else g_queuedBits[q.gpuAmps] |= 1ULL << b;
+    }
 }
 
 static bool rankBitsPinned(Qureg q) {
     auto it = g_rankBitsPinned.find(q.gpuAmps);
     return it != g_rankBitsPinned.end() && it->second;
+}
+
+static unsigned long long queuedBits(Qureg q) {
+    auto it = g_queuedBits.find(q.gpuAmps);
+    return it == g_queuedBits.end() ? 0ULL : it->second;
+}
+
+// called where all ranks stand at the same point of the program: after it no rank holds a deferred gate of q
+static void collectiveFlush(Qureg q) {
+    if (!q.isDistributed || !q.isGpuAccelerated || q.isDensityMatrix || q.gpuAmps == nullptr) return;
+    if (g_queuedBits.empty() && g_rankBitsPinned.empty()) return;
+    QB_CHECK( qb_flush() );
+    g_queuedBits.erase(q.gpuAmps);
+    g_rankBitsPinned.erase(q.gpuAmps);
 }
 
 static bool g_inCanonicalise = false;
@@ -207,6 +234,7 @@ static QubitMap& getMap(Qureg q) {
     if (it != g_qubitMaps.end()) return it->second;
     QubitMap m;
     m.qureg = q;
+    m.seq = ++g_mapSeq;
     m.phys.resize(q.numQubits); m.logi.resize(q.numQubits); m.lastUse.assign(q.numQubits, 0);
     for (int i = 0; i < q.numQubits; i++) m.phys[i] = m.logi[i] = i;
     return g_qubitMaps.emplace(q.gpuAmps, std::move(m)).first->second;
@@ -256,6 +284,9 @@ static void qbmap_canon(Qureg q) {
         canonicalise(*m);
         g_qubitMaps.erase(q.gpuAmps);
     }
+    // every rank calls this at the same point of the program (it opens each entry point that is not relabelling-aware),
+    // including those whose backend work then runs on a subset of ranks only (setQuregAmps): drain everywhere, here
+    collectiveFlush(q);
 }
 
 static void qbmap_reset(Qureg q) {
@@ -266,6 +297,7 @@ static void qbmap_reset(Qureg q) {
 void qbmap_forget(const void* gpuAmps) {
     if (!g_qubitMaps.empty()) g_qubitMaps.erase(gpuAmps);
     g_rankBitsPinned.erase(gpuAmps);
+    g_queuedBits.erase(gpuAmps);
 }
 
 void qbmap_canonicaliseHolding(const void* gpuPtr) {
@@ -277,10 +309,21 @@ void qbmap_canonicaliseHolding(const void* gpuPtr) {
     }
 }
 
+// syncQuESTEnv(): every rank is here.  The restore swaps of different Quregs are collective and do not commute with
+// each other on the wire, so the maps are visited in creation order -- the same on every rank -- never in the order of
+// the (process-specific) device pointers that key the table.
 void qbmap_canonicaliseAll() {
     if (g_inCanonicalise) return;
-    for (auto& kv : g_qubitMaps) canonicalise(kv.second);
+    std::vector<QubitMap*> order;
+    for (auto& kv : g_qubitMaps) order.push_back(&kv.second);
+    std::sort(order.begin(), order.end(), [](const QubitMap* a, const QubitMap* b) { return a->seq < b->seq; });
+    for (QubitMap* m : order) canonicalise(*m);
     g_qubitMaps.clear();
+    if (!g_queuedBits.empty() || !g_rankBitsPinned.empty()) {
+        QB_CHECK( qb_flush() );
+        g_queuedBits.clear();
+        g_rankBitsPinned.clear();
+    }
 }
 
 static void swapPrefixWithSuffix(Qureg qureg, vector<int> ctrls, vector<int> ctrlStates, int suffixTarg, int prefixTarg);
@@ -296,12 +339,13 @@ static bool pullTargetsIntoShard(Qureg qureg, QubitMap& m, vector<int>& targs, c
         qindex used = getBitMask(targs.data(), targs.size()) | getBitMask(const_cast<int*>(ctrls.data()), ctrls.size());
 
         // may the exchange overtake the gates the backend still holds back?  Only over NVLink peer memory (the NCCL
-        // path flushes anyway), and only if none of them was resolved against a rank bit; it then prefers a victim that
-        // no queued gate touches, so that the queue survives the swap-in and keeps fusing across it
+        // path flushes anyway), and only if none of them involved a rank bit; it then prefers a victim that no gate
+        // issued since the last collective flush touches, so that the queue survives the swap-in and keeps fusing
+        // across it.  `touched` is the shim's own rank-independent record (see g_queuedBits), NOT the backend's queue
         auto st = toState(qureg);
         bool mayOvertake = qb_p2p_is_available() && !rankBitsPinned(qureg);
-        unsigned long long touched = 0;
-        int queued = mayOvertake ? qb_queue_info(&st, &touched, nullptr) : 0;      // only consulted while all ranks' queues agree
+        unsigned long long touched = mayOvertake ? queuedBits(qureg) : 0;
+        int queued = touched != 0;
 
         int victim = -1;
         for (int pass = 0; pass < 4 && victim < 0; pass++) {
@@ -319,7 +363,8 @@ static bool pullTargetsIntoShard(Qureg qureg, QubitMap& m, vector<int>& targs, c
             QB_CHECK( qb_p2p_swapHalvesDeferred(&st, victim, rankWithFlipped(qureg, {targs[i]})) );
         else {
             swapPrefixWithSuffix(qureg, {}, {}, victim, targs[i]);      // flushes the queue on every rank
-            g_rankBitsPinned[qureg.gpuAmps] = false;
+            g_rankBitsPinned.erase(qureg.gpuAmps);
+            g_queuedBits.erase(qureg.gpuAmps);
         }
         int lt = m.logi[targs[i]], lv = m.logi[victim];
         m.logi[targs[i]] = lv; m.logi[victim] = lt;
@@ -337,13 +382,14 @@ static void relabelForDenseGate(Qureg qureg, vector<int>& ctrls, vector<int>& ta
         if (!mapEligible(qureg) || !qureg.isDistributed) return;
         bool prefixTarg = false;
         for (int t : targs) prefixTarg |= (t >= qureg.logNumAmpsPerNode);
-        if (!prefixTarg) { noteRankBitUse(qureg, ctrls); return; }
+        if (!prefixTarg) { noteGateQubits(qureg, ctrls); noteGateQubits(qureg, targs); return; }
         m = &getMap(qureg);
     }
     mapQubits(m, ctrls);
     mapQubits(m, targs);
     if (qureg.isDistributed) pullTargetsIntoShard(qureg, *m, targs, ctrls);
-    noteRankBitUse(qureg, ctrls);
+    noteGateQubits(qureg, ctrls);
+    noteGateQubits(qureg, targs);       // (a target left on a rank bit -- no suffix qubit was free -- pins the rank bits)
 }
 
 static PauliStr mapPauliStr(QubitMap* m, PauliStr str);
@@ -357,7 +403,7 @@ static void relabelForPauli(Qureg qureg, vector<int>& ctrls, PauliStr& str) {
     relabelForDenseGate(qureg, ctrls, xy);            // translates ctrls; creates the map on first need
     QubitMap* m = findMap(qureg);
     str = mapPauliStr(m, str);
-    noteRankBitUse(qureg, paulis_getInds(str));
+    noteGateQubits(qureg, paulis_getInds(str));
 }
 
 static PauliStr mapPauliStr(QubitMap* m, PauliStr str) {
@@ -867,7 +913,7 @@ template <class T>
 void localiser_statevec_anyCtrlAnyTargAnyMatr(Qureg qureg, vector<int> ctrls, vector<int> ctrlStates, vector<int> targs, T matr, bool conj) {
     if constexpr (util_isCompMatr<T>() || util_isCompMatr1<T>() || util_isCompMatr2<T>())
         relabelForDenseGate(qureg, ctrls, targs);
-    else { QubitMap* m = findMap(qureg); mapQubits(m, ctrls); mapQubits(m, targs); noteRankBitUse(qureg, ctrls); noteRankBitUse(qureg, targs); }
+    else { QubitMap* m = findMap(qureg); mapQubits(m, ctrls); mapQubits(m, targs); noteGateQubits(qureg, ctrls); noteGateQubits(qureg, targs); }
     if constexpr (util_isDiagMatr <T>()) phys_statevec_anyCtrlAnyTargDiagMatr(qureg,  ctrls, ctrlStates, targs, matr, 1, conj);
     if constexpr (util_isDiagMatr1<T>()) phys_statevec_anyCtrlOneTargDiagMatr(qureg,  ctrls, ctrlStates, targs[0], matr, conj);
     if constexpr (util_isDiagMatr2<T>()) phys_statevec_anyCtrlTwoTargDiagMatr(qureg,  ctrls, ctrlStates, targs[0], targs[1], matr, conj);
@@ -1497,8 +1543,9 @@ void localiser_statevec_anyCtrlSwap(Qureg qureg, vector<int> ctrls, vector<int> 
     }
     QubitMap* m = findMap(qureg);
     mapQubits(m, ctrls);
-    noteRankBitUse(qureg, ctrls);
-    phys_statevec_anyCtrlSwap(qureg, ctrls, ctrlStates, mapQubit(m, targ1), mapQubit(m, targ2));
+    int t1 = mapQubit(m, targ1), t2 = mapQubit(m, targ2);
+    noteGateQubits(qureg, ctrls); noteGateQubits(qureg, {t1, t2});
+    phys_statevec_anyCtrlSwap(qureg, ctrls, ctrlStates, t1, t2);
 }
 
 void localiser_statevec_anyCtrlOneTargDenseMatr(Qureg qureg, vector<int> ctrls, vector<int> ctrlStates, int targ, CompMatr1 matr, bool conj) {
@@ -1522,7 +1569,7 @@ void localiser_statevec_anyCtrlOneTargDiagMatr(Qureg qureg, vector<int> ctrls, v
     QubitMap* m = findMap(qureg);
     mapQubits(m, ctrls);
     int t = mapQubit(m, targ);
-    noteRankBitUse(qureg, ctrls); noteRankBitUse(qureg, {t});
+    noteGateQubits(qureg, ctrls); noteGateQubits(qureg, {t});
     phys_statevec_anyCtrlOneTargDiagMatr(qureg, ctrls, ctrlStates, t, matr, conj);
 }
 
@@ -1530,7 +1577,7 @@ void localiser_statevec_anyCtrlTwoTargDiagMatr(Qureg qureg, vector<int> ctrls, v
     QubitMap* m = findMap(qureg);
     mapQubits(m, ctrls);
     int t1 = mapQubit(m, targ1), t2 = mapQubit(m, targ2);
-    noteRankBitUse(qureg, ctrls); noteRankBitUse(qureg, {t1, t2});
+    noteGateQubits(qureg, ctrls); noteGateQubits(qureg, {t1, t2});
     phys_statevec_anyCtrlTwoTargDiagMatr(qureg, ctrls, ctrlStates, t1, t2, matr, conj);
 }
 
@@ -1538,7 +1585,7 @@ void localiser_statevec_anyCtrlAnyTargDiagMatr(Qureg qureg, vector<int> ctrls, v
     QubitMap* m = findMap(qureg);
     mapQubits(m, ctrls);
     mapQubits(m, targs);
-    noteRankBitUse(qureg, ctrls); noteRankBitUse(qureg, targs);
+    noteGateQubits(qureg, ctrls); noteGateQubits(qureg, targs);
     phys_statevec_anyCtrlAnyTargDiagMatr(qureg, ctrls, ctrlStates, targs, matr, exponent, conj);
 }
 
@@ -1551,7 +1598,7 @@ void localiser_statevec_anyCtrlPhaseGadget(Qureg qureg, vector<int> ctrls, vecto
     QubitMap* m = findMap(qureg);
     mapQubits(m, ctrls);
     mapQubits(m, targs);
-    noteRankBitUse(qureg, ctrls); noteRankBitUse(qureg, targs);
+    noteGateQubits(qureg, ctrls); noteGateQubits(qureg, targs);
     phys_statevec_anyCtrlPhaseGadget(qureg, ctrls, ctrlStates, targs, phase);
 }
 

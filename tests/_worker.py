@@ -44,6 +44,7 @@ def main():
             import ctypes
             core = ctypes.CDLL(os.path.join(os.path.dirname(qa.B200_LIB), "libquest_b200.so"), mode=ctypes.RTLD_GLOBAL)
             out["p2p_available"] = int(core.qb_p2p_is_available())
+            out["transport"] = int(core.qb_comm_transport())
         outs.append(out)
     Q.finalizeQuESTEnv()
     pickle.dump(outs, open(dst, "wb"))

@@ -60,7 +60,7 @@ def assert_outputs_match(got, want, tol=TOL, label="", int_exact_ops=()):
             continue
         scale = max(1.0, float(np.max(np.abs(wf)))) if wf.size else 1.0
         err = float(np.max(np.abs(gf - wf))) if wf.size else 0.0
-        assert err <= tol * scale * 10, f"{label} result {i}: {g} vs {w} (abs err {err:.3e})"
+        assert err <= tol * scale, f"{label} result {i}: {g} vs {w} (abs err {err:.3e})"
 
 
 def load_golden(name):
@@ -87,7 +87,8 @@ def run_programs_distributed(progs, world, timeout=420, env=None, port=29731):
         for r in range(world):
             e = dict(os.environ)
             e.update(env or {})
-            e.update(RANK=str(r), WORLD_SIZE=str(world), LOCAL_RANK=str(r), MASTER_ADDR="127.0.0.1", MASTER_PORT=str(port),
+            # fewer GPUs than ranks: ranks share devices and the backend switches to its shared-memory / CUDA-IPC transport
+            e.update(RANK=str(r), WORLD_SIZE=str(world), LOCAL_RANK=str(r % max(1, num_gpus())), MASTER_ADDR="127.0.0.1", MASTER_PORT=str(port),
                      QUEST_B200_ID_FILE=os.path.join(d, "nccl_id"))
             procs.append(subprocess.Popen([sys.executable, os.path.join(ROOT, "tests", "_worker.py"), "b200dist", src, dst],
                                           stdout=subprocess.PIPE, stderr=subprocess.PIPE, text=True, env=e))

@@ -347,3 +347,75 @@ def relabel_program(n, seed, num_ops=160, reads=True):
                 ops.append(["calcTotalProb", "psi"])
     ops.append(["calcTotalProb", "psi"])
     return {"quregs": {"psi": {"n": n, "init": ["amps", enc_mat(rand_state(rng, n))]}}, "ops": ops, "dump": ["psi"]}
+
+
+def rank_divergence_program(n, logp, seed, num_rounds=12):
+    """Operations after which the ranks' deferred-gate queues DIFFER -- setQuregAmps of a few amplitudes (runs on the
+    owning ranks only), a controlled SWAP of two rank-bit qubits (runs on the ranks whose two bits differ), gates with
+    rank-bit controls (dropped on half of the ranks) -- each followed by dense gates on rank-bit qubits, whose swap-in
+    victim must still be chosen identically on every rank.  n - logp local qubits; the top logp are rank bits."""
+    rng = np.random.default_rng(seed)
+    nl = n - logp
+    ops = []
+    for _ in range(num_rounds):
+        # leave gates in the queue that touch the HIGH suffix qubits (the preferred swap-in victims)
+        for _ in range(int(rng.integers(1, 4))):
+            ops.append(["applyCompMatr1", "psi", int(rng.integers(max(0, nl - 3), nl)), {"m1": enc_mat(rand_unitary(rng, 2))}])
+        which = int(rng.integers(4))
+        if which == 0:
+            k = int(rng.integers(1, 4))
+            start = int(rng.integers(0, (1 << n) - k))
+            vals = rng.normal(size=k) + 1j * rng.normal(size=k)
+            ops.append(["setQuregAmps", "psi", start, {"amps": enc_mat(0.1 * vals)}, k])
+        elif which == 1 and logp >= 2:
+            a, b = [nl + int(x) for x in rng.choice(logp, size=2, replace=False)]
+            c = int(rng.integers(nl))
+            ops.append(["applyMultiStateControlledSwap", "psi", [c], [int(rng.integers(2))], 1, a, b])
+        elif which == 2:
+            c = nl + int(rng.integers(logp))
+            ops.append(["applyMultiStateControlledCompMatr1", "psi", [c], [int(rng.integers(2))], 1, int(rng.integers(nl)),
+                        {"m1": enc_mat(rand_unitary(rng, 2))}])
+        else:
+            a, b = _pick(rng, n, 2)
+            ops.append(["applySwap", "psi", a, b])
+        # now gates whose targets sit on rank bits (or were relabelled there)
+        for _ in range(int(rng.integers(1, 3))):
+            ops.append(["applyCompMatr1", "psi", nl + int(rng.integers(logp)), {"m1": enc_mat(rand_unitary(rng, 2))}])
+        a, b = _pick(rng, n, 2)
+        ops.append(["applyCompMatr2", "psi", a, b, {"m2": enc_mat(rand_unitary(rng, 4))}])
+    ops.append(["calcTotalProb", "psi"])
+    return {"quregs": {"psi": {"n": n, "init": ["amps", enc_mat(rand_state(rng, n))]}}, "ops": ops, "dump": ["psi"]}
+
+
+def coevolution_program(n, seed, num_ops=60):
+    """The reference's psi / rho co-evolution pattern (tests/integration/densitymatrix.cpp:68-163): the same random
+    gates applied alternately to a statevector and to a density matrix, which are then compared through
+    calcFidelity.  For the backend this interleaves fusable gates on two (here three) different Quregs."""
+    rng = np.random.default_rng(seed)
+    ops = []
+    for _ in range(num_ops):
+        r = int(rng.integers(5))
+        if r == 0:
+            t = int(rng.integers(n))
+            for name in ("psi", "rho", "phi"):
+                ops.append(["applyHadamard", name, t])
+        elif r == 1:
+            t = int(rng.integers(n)); m = {"m1": enc_mat(rand_unitary(rng, 2))}
+            for name in ("psi", "rho", "phi"):
+                ops.append(["applyCompMatr1", name, t, m])
+        elif r == 2:
+            a, b = _pick(rng, n, 2); m = {"m2": enc_mat(rand_unitary(rng, 4))}
+            for name in ("psi", "rho", "phi"):
+                ops.append(["applyCompMatr2", name, a, b, m])
+        elif r == 3:
+            a, b = _pick(rng, n, 2)
+            for name in ("psi", "rho", "phi"):
+                ops.append(["applyControlledPauliX", name, a, b])
+        elif r == 4:
+            a, b = _pick(rng, n, 2); th = float(rng.uniform(0, 6))
+            for name in ("psi", "rho", "phi"):
+                ops.append(["applyTwoQubitPhaseShift", name, a, b, th])
+    ops.append(["calcFidelity", "rho", "psi"])
+    ops.append(["calcTotalProb", "phi"])
+    return {"quregs": {"psi": {"n": n, "init": "zero"}, "rho": {"n": n, "dm": 1, "init": "zero"}, "phi": {"n": n, "init": "plus"}},
+            "ops": ops, "dump": ["psi", "rho", "phi"]}
