@@ -2,7 +2,7 @@
 #
 #   make kernels   -> quest_b200/lib/libquest_b200.so   hand-written sm_100a CUDA + the C ABI (include/quest_b200.h)
 #   make quest     -> quest_b200/lib/libQuEST.so        the drop-in: QuEST v4.1.0's unmodified host layers
-#                                                        (api/ core/ cpu/, compiled from $(REF) where they lie)
+#                                                        (api/ core/ cpu/, compiled from $(REF) into build/hostobj)
 #                                                        + our shim defining gpu_* / comm_* (quest_b200/shim)
 #   make oracle    -> oracle/_ref/libQuEST.so           the unmodified reference CPU/OpenMP build (parity oracle)
 #   make           -> all of the above
@@ -30,16 +30,32 @@ SHIM_OBJS := $(patsubst quest_b200/shim/%.cpp,$(BUILD)/shim/%.o,$(SHIM_SRCS))
 SHIM_DEFS := -DFLOAT_PRECISION=2 -DCOMPILE_OPENMP=1 -DCOMPILE_MPI=1 -DCOMPILE_CUDA=1 -DCOMPILE_CUQUANTUM=0
 SHIM_FLAGS := -std=c++17 -O2 -fPIC -fopenmp -Wno-unknown-pragmas -I$(REF) -Iinclude $(SHIM_DEFS)
 
-HOSTOBJ_DIR := oracle/_ref/hostobj
+# The drop-in links the reference's UNMODIFIED host layers (api/ core/ cpu/ -- the caller of the replaced backend),
+# compiled here from $(REF) where they lie into $(BUILD)/hostobj with the product's own flags; nothing under oracle/
+# (the parity checker) is part of the product build.  core/localiser.cpp, gpu/* and comm/* are NOT compiled: the shim
+# replaces them.  (accelerator.cpp dispatches to cpu_* for CPU-deployed Quregs, so the reference's CPU backend is
+# necessarily linked; the B200 backend itself has no CPU path -- see DESIGN.md.)
+HOSTOBJ_DIR := $(BUILD)/hostobj
 HAVE_REF := $(wildcard $(REF)/quest/src/api/qureg.cpp)
-# comm_* and localiser_* come from quest_b200/shim; the reference objects for those files are NOT linked
-EXTRA_REF_OBJS ?=
-LOCALISER_FILTER ?= ! -name localiser.o
+HOST_SRCS := $(wildcard $(REF)/quest/src/api/*.cpp) $(filter-out %/localiser.cpp,$(wildcard $(REF)/quest/src/core/*.cpp)) $(wildcard $(REF)/quest/src/cpu/*.cpp)
+HOST_OBJS := $(patsubst $(REF)/quest/src/%.cpp,$(HOSTOBJ_DIR)/%.o,$(HOST_SRCS))
+HOST_FLAGS := -std=c++17 -O3 -fPIC -fopenmp -Wno-unknown-pragmas -I$(REF) $(SHIM_DEFS)
 
-.PHONY: all kernels quest oracle clean
+.PHONY: all kernels selftest quest oracle clean
 all: kernels oracle quest
 
-kernels: $(LIBDIR)/libquest_b200.so
+kernels: $(LIBDIR)/libquest_b200.so selftest
+
+# test-only twin of the kernel library: the two translation units that hold host-side self-tests are recompiled with
+# -DQB_SELFTEST (include/quest_b200_selftest.h); the product library above is built WITHOUT them
+selftest: $(LIBDIR)/libquest_b200_selftest.so
+SELFTEST_UNITS := qb_tile qb_runtime
+SELFTEST_OBJS  := $(patsubst %,$(BUILD)/selftest/%.o,$(SELFTEST_UNITS))
+$(BUILD)/selftest/%.o: quest_b200/csrc/%.cu $(CU_HDRS) include/quest_b200_selftest.h
+	@mkdir -p $(dir $@)
+	$(NVCC) $(NVFLAGS) -DQB_SELFTEST -I$(NCCL_INC) -c $< -o $@
+$(LIBDIR)/libquest_b200_selftest.so: $(SELFTEST_OBJS) $(CU_OBJS)
+	$(NVCC) $(ARCH) -shared -o $@ $(SELFTEST_OBJS) $(filter-out $(patsubst %,$(BUILD)/csrc/%.o,$(SELFTEST_UNITS)),$(CU_OBJS)) -L$(NCCL_LIB) -lnccl
 
 $(BUILD)/csrc/%.o: quest_b200/csrc/%.cu $(CU_HDRS)
 	@mkdir -p $(dir $@)
@@ -58,17 +74,16 @@ quest:
 else
 quest: $(LIBDIR)/libQuEST.so
 
-# host-layer objects of the reference are shared with the oracle build (oracle/Makefile explains why that is sound)
-HOST_OBJS = $(filter-out %/core/localiser.o,$(shell find $(HOSTOBJ_DIR) -name '*.o' 2>/dev/null))
+$(HOSTOBJ_DIR)/%.o: $(REF)/quest/src/%.cpp
+	@mkdir -p $(dir $@)
+	$(CXX) $(HOST_FLAGS) -c $< -o $@
 
 $(BUILD)/shim/%.o: quest_b200/shim/%.cpp include/quest_b200.h $(wildcard quest_b200/shim/*.hpp)
 	@mkdir -p $(dir $@)
 	$(CXX) $(SHIM_FLAGS) -c $< -o $@
 
-$(LIBDIR)/libQuEST.so: $(SHIM_OBJS) $(LIBDIR)/libquest_b200.so | oracle
-	$(MAKE) -C oracle hostobjs
-	$(CXX) -shared -fopenmp -o $@ $(SHIM_OBJS) $$(find $(HOSTOBJ_DIR) -name '*.o' $(LOCALISER_FILTER)) $(EXTRA_REF_OBJS) \
-	    -L$(LIBDIR) -lquest_b200 -Wl,-rpath,'$$ORIGIN'
+$(LIBDIR)/libQuEST.so: $(SHIM_OBJS) $(HOST_OBJS) $(LIBDIR)/libquest_b200.so
+	$(CXX) -shared -fopenmp -o $@ $(SHIM_OBJS) $(HOST_OBJS) -L$(LIBDIR) -lquest_b200 -Wl,-rpath,'$$ORIGIN'
 endif
 
 clean:

@@ -1,29 +1,33 @@
 #!/usr/bin/env python
-"""bench.py -- the reference's headline workload on the B200 backend (BASELINE.json cfg 2).
+"""bench.py -- the reference's headline workload on the B200 backend (BASELINE.json cfg 2), 1..8 GPUs of one box.
 
-workload (N=1): 30-qubit fp64 statevector; one STEP = applyFullQuantumFourierTransform (30 H + 435
-controlled phase shifts + 15 SWAPs, api/operations.cpp:1934-1953) followed by 200 random dense 1- and
-2-qubit unitaries on uniformly random targets (seed 20302) = 680 gates per step.
-For N>1 GPUs the state has 30+log2(N) qubits sharded over the ranks (2^30 amplitudes per GPU, weak scaling).
+workload: a (30 + log2 N)-qubit fp64 statevector, 2^30 amplitudes per GPU (weak scaling; N=1 is BASELINE's 30-qubit
+configuration).  One STEP = applyFullQuantumFourierTransform (30+ H, the controlled-phase ladders, n/2 SWAPs;
+api/operations.cpp:1934-1953) + 200 random dense 1- and 2-qubit unitaries on uniformly random targets (seed 20302,
+SURVEY.md 8d) + syncQuESTEnv().  Every arm and every N drives QuEST's PUBLIC API (the call a user makes): the product
+arm on the drop-in quest_b200/lib/libQuEST.so (sharding shim + deferred gate queue + sm_100a kernels all on the measured
+path), the reference arm on the unmodified CPU/OpenMP build oracle/_ref/libQuEST.so.
 
-Both timings drive QuEST's public API on the drop-in libQuEST.so (the call a user makes; the reference-facing
-boundary), so the sharding shim, the deferred gate queue and the kernels are all on the measured path.
-
-  value   gates/s with the state resident in HBM, CUDA events on the backend's stream.  The timed region is
-          K x (QFT + 200 dense gates) and ENDS with syncQuESTEnv(): the backend defers work (fusable gates are queued,
-          uncontrolled SWAPs only relabel qubits), and syncQuESTEnv() is what guarantees nothing is left undone
-          (it restores the canonical qubit order and drains the stream).  N>1: the unit is one gate applied to one
-          2^30-amplitude shard, so value = N x circuit gates / step time (quest_b200/dist_bench.py).
-  e2e     the same metric end to end with HOST buffers: initZeroState, the circuit (every matrix travels host ->
-          device inside its call), calcProbOfQubitOutcome read back device -> host; host wall clock.  A statevector
-          simulator's state is created on the device by the reference's own API (createQureg/initZeroState,
-          api/qureg.cpp:143-174) and never crosses PCIe; its per-step host inputs are the gate operands.
-  roofline   the dense-gate section: algorithmic bytes of its 200 gates (2*16*2^30 each) / CUDA-event
-          time of the section, against MEASURED_PEAKS.json hbm_gbs; frac > 1 is the gain of fusing several gates into
-          one HBM pass; physical_frac is the traffic actually moved (one read + one write of the state per launch,
-          confirmed by ncu in profiles/) against the same peak.
-  cpu_baseline / --impl reference: the UNMODIFIED reference CPU/OpenMP library (oracle/_ref/libQuEST.so) on the
-          box's host cores, timed on a bounded stratified sample of the same 680-gate stream at the same size.
+  metric  "30q fp64 gates/s" -- the unit is ONE gate applied to ONE 2^30-amplitude shard; at N GPUs every circuit gate
+          acts on N shards, so value = N x gates per step / step time.  The same string at every N and in both arms.
+  value   state resident in HBM, CUDA events on the backend's stream, max over ranks.  The backend defers work (fusable
+          gates are queued, uncontrolled SWAPs only relabel qubits), so every timed step ENDS with syncQuESTEnv(), which
+          drains the queue and restores the canonical qubit order: each step is complete, observable work.
+  e2e     the same step end to end with HOST buffers: initZeroState, every gate operand travelling host -> device
+          inside its API call, calcProbOfQubitOutcome read back device -> host; host wall clock, max over ranks.
+          (A statevector never crosses PCIe in QuEST -- createQureg/initZeroState build it on the device,
+          api/qureg.cpp:143-174 -- so the per-step host inputs are the gate matrices and angles.)
+  roofline  dominant kernel k_tile_pass (the fused multi-gate pass): achieved = algorithmic bytes of the step's gates
+          (2*16*2^30 / 2^controls each) / step time, against MEASURED_PEAKS.json hbm_gbs.  frac > 1 is the
+          gain of applying several gates per pass over HBM; physical_frac is the traffic actually moved (one read + one
+          write of the shard per launch; `traffic` = ncu's dram bytes per launch, profiles/); fp64_frac is the share of the
+          FP64 pipe's measured peak the executed fused multiply-adds amount to -- the pass is FP64/shared-memory bound,
+          not HBM bound, once it fuses more than ~3 gates.  N>1 adds `nvlink` (bytes each GPU sent per direction / time
+          spent exchanging, against 900 GB/s).
+  cpu_baseline / --impl reference   the UNMODIFIED reference on the box's host cores, all threads, on a bounded sample of
+          the same gate stream (every k-th gate of the 680) at 30 qubits = the metric's unit.
+  secondary  the other BASELINE configurations measured in the same run (cfg 3: random circuit at 2^31 amplitudes per GPU,
+          i.e. 34 qubits on 8 GPUs; cfg 4: 14-qubit noisy density matrix; cfg 5: 28-qubit Trotter + 200-term Pauli sum).
 """
 import argparse
 import ctypes as C
@@ -43,10 +47,13 @@ sys.path.insert(0, ROOT)
 SEED = 20302
 NUM_DENSE = 200
 AMP_BYTES = 16
+METRIC = "30q fp64 gates/s"
+FP64_PEAK_TFLOPS = 36.9          # measured on this pool's B200s with tools/dfma_probe.cu (profiles/r1_fp64_probe.txt)
+NVLINK_PEAK_GBS = 900.0          # per direction per GPU (BASELINE.md / north star)
 
 
 # ------------------------------------------------------------------------------------------------
-# the gate stream (identical for every arm)
+# the gate streams (identical for every arm; tests/test_fullsize_gpu.py replays them against the reference)
 # ------------------------------------------------------------------------------------------------
 def rand_unitary(rng, dim):
     z = rng.normal(size=(dim, dim)) + 1j * rng.normal(size=(dim, dim))
@@ -105,6 +112,23 @@ def algorithmic_bytes(op, local_amps):
     """a gate on N local amps with c controls reads+writes 2*B*N/2^c; SWAP counts as c=1."""
     full = 2 * AMP_BYTES * local_amps
     return full // 2 if op[0] in ("cphase", "swap", "cnot") else full
+
+
+def build_config(n_local, world, workload="cfg2", cpu_sample=24):
+    """the `config` object -- a pure function of the workload, so both arms print the same one"""
+    n = n_local + int(math.log2(max(1, world)))
+    if workload == "cfg3":
+        return {"workload": f"cfg3: {n}q fp64 statevector, initPlusState + 100 random gates from {{H, Rx, CompMatr1, CNOT, CompMatr2}}, targets uniform over all qubits",
+                "qubits": n, "amps_per_gpu": 1 << n_local, "gates_per_step": 100, "seed": 34008,
+                "l2_policy": "state per GPU is far larger than L2; every pass streams it from HBM"}
+    gates = len(qft_stream(n)) + NUM_DENSE
+    return {"workload": f"cfg2: {n}q fp64 statevector ({1 << int(math.log2(max(1, world)))} x 2^{n_local} amplitudes), applyFullQuantumFourierTransform + {NUM_DENSE} random dense 1/2-qubit gates + syncQuESTEnv per step",
+            "qubits": n, "amps_per_gpu": 1 << n_local, "gates_per_step": gates, "seed": SEED,
+            "gates_per_step_without_relabelled_swaps": gates - n // 2,
+            "unit": f"one gate applied to one 2^{n_local}-amplitude shard (a circuit gate counts once per GPU)",
+            "l2_policy": "state (16 GiB per GPU) is far larger than L2; every pass streams it from HBM",
+            "reference_arm": f"unmodified CPU/OpenMP reference at {n_local} qubits (the metric's unit) on every {max(1, (len(qft_stream(n_local)) + NUM_DENSE) // cpu_sample)}th gate "
+                             f"of the {len(qft_stream(n_local)) + NUM_DENSE}-gate stream ({cpu_sample} gates per step), all host threads"}
 
 
 # ------------------------------------------------------------------------------------------------
@@ -189,7 +213,9 @@ for s in range(warmup + steps):
     dt = time.perf_counter() - t0
     if s >= warmup: times.append(dt); gates.append(done)
 prob = Q.calcTotalProb(q)
-print("REFJSON " + json.dumps(dict(times=times, gates=gates, prob=prob, stride=stride, threads=int(os.environ.get("OMP_NUM_THREADS", "1")))))
+kinds = dict()
+for op in sample: kinds[op[0]] = kinds.get(op[0], 0) + 1
+print("REFJSON " + json.dumps(dict(times=times, gates=gates, prob=prob, stride=stride, kinds=kinds, threads=int(os.environ.get("OMP_NUM_THREADS", "1")))))
 """
 
 
@@ -203,8 +229,8 @@ def run_reference(n, steps, warmup, sample_size, budget_s):
             d = json.loads(line[8:])
             total_t, total_g = sum(d["times"]), sum(d["gates"])
             return {"value": total_g / total_t, "unit": "gates/s", "cores": cores, "kind": "reference",
-                    "sample": f"{d['gates'][0]} gates/step: every {d['stride']}th gate of the 680-gate cfg-2 stream at {n} qubits, "
-                              f"{len(d['times'])} timed step(s), OMP_NUM_THREADS={cores}",
+                    "sample": f"{d['gates'][0]} gates/step: every {d['stride']}th gate of the {len(qft_stream(n)) + NUM_DENSE}-gate cfg-2 stream at {n} qubits "
+                              f"({d['kinds']}), {len(d['times'])} timed step(s), OMP_NUM_THREADS={cores}",
                     "ms_per_step": 1e3 * total_t / len(d["times"]), "total_prob": d["prob"]}
     raise RuntimeError(f"reference worker failed rc={r.returncode}\n{r.stdout[-2000:]}\n{r.stderr[-2000:]}")
 
@@ -212,6 +238,364 @@ def run_reference(n, steps, warmup, sample_size, budget_s):
 # ------------------------------------------------------------------------------------------------
 # the product arm
 # ------------------------------------------------------------------------------------------------
+class Product:
+    """the drop-in library driven through QuEST's public API, on 1..8 ranks"""
+
+    def __init__(self, rank, world, local_rank):
+        import torch
+        from quest_b200 import capi, quest_api as qa
+        self.torch, self.capi, self.rank, self.world = torch, capi, rank, world
+        if not torch.cuda.is_available():
+            raise SystemExit("bench.py: no CUDA device; the quest_b200 backend has no CPU fallback")
+        torch.cuda.set_device(local_rank)
+        self.dev = torch.device("cuda", local_rank)
+        self.dist = None
+        if world > 1:
+            import torch.distributed as dist
+            dist.init_process_group("nccl", device_id=self.dev)
+            self.dist = dist
+        capi.call("qb_bind_device", local_rank)
+        if world > 1:
+            # the backend's own NCCL communicator: its unique id travels over torch.distributed (control plane only)
+            idbuf = (C.c_char * 128)()
+            if rank == 0:
+                capi.call("qb_comm_get_unique_id", idbuf)
+            t = torch.tensor(list(bytes(idbuf)), dtype=torch.uint8, device=self.dev)
+            self.dist.broadcast(t, src=0)
+            os.environ["QUEST_B200_NCCL_ID"] = bytes(t.cpu().tolist()).hex()
+        self.Q = qa.QuEST(qa.B200_LIB)
+        self.Q.initCustomQuESTEnv(1 if world > 1 else 0, 1, 0)
+        self.lib = capi.lib()
+
+    def barrier(self):
+        self.torch.cuda.synchronize()
+        if self.dist:
+            self.dist.barrier()
+
+    def max_over_ranks(self, x):
+        if not self.dist:
+            return float(x)
+        t = self.torch.tensor([float(x)], dtype=self.torch.float64, device=self.dev)
+        self.dist.all_reduce(t, op=self.dist.ReduceOp.MAX)
+        return t.item()
+
+    def create(self, n, dm=0):
+        q = self.Q.createCustomQureg(n, dm, 1 if self.world > 1 else 0, 1, 0)
+        assert q.isGpuAccelerated == 1 and q.numNodes == self.world
+        return q
+
+    def stats(self):
+        s = (C.c_double * 6)()
+        self.lib.qb_tile_stats(s)
+        a, b = C.c_ulonglong(), C.c_ulonglong()
+        self.lib.qb_p2p_stats(C.byref(a), C.byref(b))
+        return {"launches": self.lib.qb_launch_count(), "passes": s[0], "rounds": s[1], "tile_ops": s[2], "direct_ops": s[3],
+                "fma": s[5], "exchanges": a.value, "link_bytes": b.value}
+
+    def gate(self, q, op, m=None):
+        Q = self.Q
+        k = op[0]
+        if k == "m1": Q.applyCompMatr1(q, op[1], m)
+        elif k == "m2": Q.applyCompMatr2(q, op[1], op[2], m)
+        elif k == "h": Q.applyHadamard(q, op[1])
+        elif k == "rx": Q.applyRotateX(q, op[1], op[2])
+        elif k == "cnot": Q.applyControlledPauliX(q, op[1], op[2])
+        elif k == "cphase": Q.applyTwoQubitPhaseShift(q, op[1], op[2], op[3])
+        elif k == "swap": Q.applySwap(q, op[1], op[2])
+        else: raise ValueError(k)
+
+    def mats(self, ops):
+        Q = self.Q
+        return [(op, Q.getCompMatr1(op[2]) if op[0] == "m1" else (Q.getCompMatr2(op[3]) if op[0] == "m2" else None)) for op in ops]
+
+    def timed(self, fn, steps, warmup):
+        """warm up, then time `steps` calls of fn with CUDA events on the backend's stream (the legacy default stream,
+        which is torch's current stream), barrier + synchronize on both sides, max over ranks -> ms per call"""
+        torch = self.torch
+        for _ in range(warmup):
+            fn()
+        self.barrier()
+        e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        e0.record()
+        for _ in range(steps):
+            fn()
+        e1.record()
+        self.barrier()
+        return self.max_over_ranks(e0.elapsed_time(e1)) / steps
+
+
+def secondary_configs(P, n_local, full):
+    """the other BASELINE configurations, through the public API, device-timed (events) incl. the final syncQuESTEnv"""
+    from quest_b200.program import _Interp
+    from tests import programs as TP
+    Q, world = P.Q, P.world
+    logw = int(math.log2(world))
+    out = {}
+
+    # cfg 3: random circuit, 2^31 amplitudes per GPU (34 qubits on 8 GPUs); on 4 GPUs additionally 34 qubits (2^32 per GPU)
+    sizes = [31 + logw] + ([34] if world == 4 and full else [])
+    for n3 in sizes:
+        try:
+            q = P.create(n3)
+        except Exception as exc:      # not enough memory on this box: report, never fake
+            out[f"cfg3_{n3}q"] = {"error": str(exc)[:200]}
+            continue
+        ops = P.mats(cfg3_stream(n3))
+
+        def circuit():
+            Q.initPlusState(q)
+            for op, m in ops:
+                P.gate(q, op, m)
+            Q.syncQuESTEnv()
+        s0 = P.stats()
+        ms = P.timed(circuit, 2, 1)
+        s1 = P.stats()
+        prob = Q.calcTotalProb(q)
+        Q.destroyQureg(q)
+        out[f"cfg3_{n3}q"] = {"workload": f"cfg3: {n3}q random circuit (100 gates from {{H,Rx,CompMatr1,CNOT,CompMatr2}}, seed 34008) incl. initPlusState + syncQuESTEnv",
+                              "n_gpus": world, "ms_per_circuit": ms, "circuit_gates_per_s": 100 / (ms * 1e-3), "exchanges_per_circuit": (s1["exchanges"] - s0["exchanges"]) / 3,
+                              "link_bytes_per_dir_per_circuit": (s1["link_bytes"] - s0["link_bytes"]) / 3, "launches_per_circuit": (s1["launches"] - s0["launches"]) / 3,
+                              "total_prob": prob}
+
+    def run_prog(prog, reps):
+        """time a tests/programs.py program (creation and destruction of its Quregs excluded, everything else included)"""
+        for spec in prog["quregs"].values():
+            spec["custom"] = [1 if world > 1 else 0, 1, 0]
+        it = _Interp(Q, dict(prog, dump=[]))
+        # split: create quregs once, then time the op list
+        quregs = {}
+        for name, spec in prog["quregs"].items():
+            quregs[name] = Q.createCustomQureg(int(spec["n"]), int(spec.get("dm", 0)), *spec["custom"])
+        it.quregs = quregs
+        results = []
+
+        def body():
+            for name, spec in prog["quregs"].items():
+                Q.initPlusState(quregs[name])
+            results.clear()
+            for op in prog["ops"]:
+                it.keep, it.outarr = [], None
+                cargs = [it.conv(a) for a in op[1:]]
+                r = getattr(Q.lib, op[0])(*cargs)
+                results.append(r)
+                for fn, obj in it.cleanup:
+                    getattr(Q.lib, fn)(obj)
+                it.cleanup.clear()
+            Q.syncQuESTEnv()
+        ms = P.timed(body, reps, 1)
+        for qq in quregs.values():
+            Q.destroyQureg(qq)
+        return ms, list(results)
+
+    # cfg 4: 14-qubit density matrix (2^28 amplitudes in total), 10 noisy layers + projector + trace + purity
+    prog = TP.cfg4_program(14, 14014, layers=10, dump=False)
+    nops = sum(1 for op in prog["ops"] if op[0].startswith(("apply", "mix")))
+    ms, res = run_prog(prog, 2)
+    out["cfg4_14q_density_matrix"] = {"workload": "cfg4: 14q density matrix, 10 layers of (H x14, CNOT chain, mixDepolarising x14, 2-qubit mixKrausMap x7) + applyMultiQubitProjector + calcTotalProb + calcPurity",
+                                      "n_gpus": world, "ms_per_circuit": ms, "ops": nops, "ops_per_s": nops / (ms * 1e-3),
+                                      "algorithmic_gbs_per_gpu": nops * 2 * AMP_BYTES * (1 << 28) / world / (ms * 1e-3) / 1e9,
+                                      "total_prob": res[-2], "purity": res[-1]}
+
+    # cfg 5: 28 qubits, 400 Pauli gadgets (2nd-order Trotter of a 200-term Hamiltonian) then calcExpecPauliStrSum
+    prog = TP.cfg5_program(28, 28200, num_terms=200, dump=False)
+    ms_t, _ = run_prog(dict(prog, ops=[prog["ops"][0]]), 2)
+    ms_e, res = run_prog(dict(prog, ops=[prog["ops"][1]]), 2)
+    out["cfg5_28q_trotter_paulisum"] = {"workload": "cfg5: 28q, applyTrotterizedPauliStrSumGadget (order 2, 400 gadgets) and calcExpecPauliStrSum (200 terms), each incl. initPlusState + syncQuESTEnv",
+                                        "n_gpus": world, "trotter_ms": ms_t, "gadgets_per_s": 400 / (ms_t * 1e-3), "expec_ms": ms_e,
+                                        "expec_algorithmic_gbs_per_gpu": 200 * AMP_BYTES * (1 << 28) / world / (ms_e * 1e-3) / 1e9, "expec_value": res[0]}
+    return out
+
+
+def run_product(args, rank, world, local_rank):
+    P = Product(rank, world, local_rank)
+    Q, torch, capi = P.Q, P.torch, P.capi
+    n_local = args.qubits or 30
+    logw = int(math.log2(world))
+    n = n_local + logw
+    local_amps = 1 << n_local
+    config = build_config(n_local, world, args.workload, args.cpu_sample)
+    cfg3 = args.workload == "cfg3"
+
+    qft = [] if cfg3 else qft_stream(n)
+    dense_ops = cfg3_stream(n) if cfg3 else dense_stream(n)
+    dense = P.mats(dense_ops)
+    num_gates = len(qft) + len(dense)
+    bytes_step = sum(algorithmic_bytes(op, local_amps) for op in qft) + sum(algorithmic_bytes(op, local_amps) for op in dense_ops)
+    qureg = P.create(n)
+
+    def circuit():
+        if not cfg3:
+            Q.applyFullQuantumFourierTransform(qureg)
+        for op, m in dense:
+            P.gate(qureg, op, m)
+
+    def step():                       # one complete step: nothing deferred, canonical qubit order restored
+        circuit()
+        Q.syncQuESTEnv()
+
+    # ---------------- device-resident timing ----------------
+    Q.initPlusState(qureg)
+    for _ in range(args.warmup):
+        step()
+    P.barrier()
+    sampler = ClockSampler(local_rank)
+    if rank == 0:
+        sampler.start()
+    s0 = P.stats()
+    ms_per_step = P.timed(step, args.steps, 0)
+    s1 = P.stats()
+    clocks = sampler.stop() if rank == 0 else None
+    launches = s1["launches"] - s0["launches"]
+    total_prob = Q.calcTotalProb(qureg)
+
+    # ---------------- e2e: + state initialisation, host operands in, a probability read back ----------------
+    e2e = None
+    if not args.no_e2e:
+        h2d = sum(64 if op[0] == "m1" else (256 if op[0] == "m2" else 16) for op in dense_ops) + 32 * sum(1 for op in qft if op[0] != "swap")
+
+        def e2e_step():
+            Q.initPlusState(qureg) if cfg3 else Q.initZeroState(qureg)
+            circuit()
+            p = Q.calcProbOfQubitOutcome(qureg, n - 1, 0)          # device -> host read of the step's result
+            Q.syncQuESTEnv()
+            return p
+
+        for _ in range(min(args.warmup, 2)):
+            e2e_step()
+        P.barrier()
+        t0 = time.perf_counter()
+        for _ in range(args.steps):
+            prob = e2e_step()
+        P.barrier()
+        dt = P.max_over_ranks(time.perf_counter() - t0)
+        e2e = {"value": world * num_gates * args.steps / dt, "unit": "gates/s", "h2d_bytes_per_step": h2d, "d2h_bytes_per_step": 8,
+               "ms_per_step": 1e3 * dt / args.steps, "result_prob_of_top_qubit_0": prob,
+               "api": "initZeroState + applyFullQuantumFourierTransform + applyCompMatr1/2 x200 + calcProbOfQubitOutcome + syncQuESTEnv"}
+
+    # ---------------- section breakdown (untimed extra steps): QFT / dense / restore, and gate-by-gate exchange cost ----------------
+    def ev():
+        return torch.cuda.Event(enable_timing=True)
+    sections = None
+    if not cfg3:
+        Q.initPlusState(qureg); Q.syncQuESTEnv(); P.barrier()
+        a, b, c, d = ev(), ev(), ev(), ev()
+        sa = P.stats()
+        a.record(); Q.applyFullQuantumFourierTransform(qureg); capi.call("qb_flush"); b.record()
+        sb = P.stats()
+        for op, m in dense:
+            P.gate(qureg, op, m)
+        capi.call("qb_flush"); c.record()
+        sc = P.stats()
+        Q.syncQuESTEnv(); d.record(); P.barrier()
+        sd = P.stats()
+        sections = {"note": "one extra step with a flush after each section (the timed steps plan the whole step at once)",
+                    "qft_ms": P.max_over_ranks(a.elapsed_time(b)), "dense_ms": P.max_over_ranks(b.elapsed_time(c)), "restore_ms": P.max_over_ranks(c.elapsed_time(d)),
+                    "qft_launches": sb["launches"] - sa["launches"], "dense_launches": sc["launches"] - sb["launches"], "restore_launches": sd["launches"] - sc["launches"],
+                    "dense_tile_passes": sc["passes"] - sb["passes"], "dense_rounds": sc["rounds"] - sb["rounds"], "dense_gates_after_absorption": (sc["tile_ops"] - sb["tile_ops"]) + (sc["direct_ops"] - sb["direct_ops"])}
+        sections["dense_algorithmic_gbs"] = sum(algorithmic_bytes(op, local_amps) for op in dense_ops) / (sections["dense_ms"] * 1e-3) / 1e9
+        sections["dense_avg_launch_ms"] = sections["dense_ms"] / max(1, sections["dense_launches"])
+        sections["dense_fp64_tflops"] = 2 * (sc["fma"] - sb["fma"]) / (sections["dense_ms"] * 1e-3) / 1e12
+    nvlink = None
+    if world > 1:
+        # exchange cost in isolation: the step again, gate by gate with a flush after each, events around the gates that
+        # made the backend exchange half-shards (a target on a rank bit is pulled into the shard, or the final restore)
+        Q.initPlusState(qureg); Q.syncQuESTEnv(); P.barrier()
+        link_ms, link_bytes, nonlocal_gates = 0.0, 0, 0
+        stream = [(op, None) for op in qft] + dense
+        recs = []
+        for op, m in stream:
+            x0 = P.stats(); a, b = ev(), ev()
+            a.record(); P.gate(qureg, op, m); capi.call("qb_flush"); b.record()
+            x1 = P.stats()
+            if x1["exchanges"] > x0["exchanges"]:
+                recs.append((a, b, x1["link_bytes"] - x0["link_bytes"]))
+        x0 = P.stats(); a, b = ev(), ev()
+        a.record(); Q.syncQuESTEnv(); b.record()
+        x1 = P.stats()
+        if x1["exchanges"] > x0["exchanges"]:
+            recs.append((a, b, x1["link_bytes"] - x0["link_bytes"]))
+        P.barrier()
+        for a, b, nb in recs:
+            link_ms += a.elapsed_time(b); link_bytes += nb; nonlocal_gates += 1
+        link_ms = P.max_over_ranks(link_ms)
+        ach = link_bytes / (link_ms * 1e-3) / 1e9 if link_ms > 0 else None
+        nvlink = {"achieved_gbs_per_dir_per_gpu": ach, "peak_gbs_per_dir": NVLINK_PEAK_GBS, "frac": (ach / NVLINK_PEAK_GBS) if ach else None,
+                  "note": "bytes this GPU sent per direction / time of the gates that exchanged (their local gate work included), unfused gate-by-gate replay",
+                  "exchanging_calls_per_step": nonlocal_gates, "exchanges_per_timed_step": (s1["exchanges"] - s0["exchanges"]) / args.steps,
+                  "link_bytes_per_dir_per_timed_step": (s1["link_bytes"] - s0["link_bytes"]) / args.steps,
+                  "min_exchange_ms_per_timed_step_at_peak": (s1["link_bytes"] - s0["link_bytes"]) / args.steps / (NVLINK_PEAK_GBS * 1e9) * 1e3}
+    Q.destroyQureg(qureg)
+
+    # ---------------- roofline of the dominant kernel ----------------
+    peaks = {}
+    try:
+        peaks = json.load(open(os.path.join(ROOT, "MEASURED_PEAKS.json")))
+    except Exception:
+        pass
+    peak_gbs, peak_src = (peaks["hbm_gbs"], "measured (MEASURED_PEAKS.json)") if "hbm_gbs" in peaks else (6650.0, "fallback (B200_PROFILING.md)")
+    traffic, traffic_src = None, None
+    try:
+        tr = json.load(open(os.path.join(ROOT, "profiles", "ncu_traffic.json")))
+        if n_local == tr.get("local_qubits"):
+            traffic, traffic_src = tr["dram_bytes_per_launch"], tr["source"]
+    except Exception:
+        pass
+    passes = (s1["passes"] + s1["direct_ops"] - s0["passes"] - s0["direct_ops"]) / args.steps
+    kernel_launches = launches / args.steps
+    achieved = bytes_step / (ms_per_step * 1e-3) / 1e9
+    physical = kernel_launches * 2 * AMP_BYTES * local_amps / (ms_per_step * 1e-3) / 1e9
+    fp64 = 2 * (s1["fma"] - s0["fma"]) / args.steps / (ms_per_step * 1e-3) / 1e12
+    roofline = {"kernel": "k_tile_pass (fused multi-gate pass over the shard; >95% of the step's device time) + the few direct single-gate kernels",
+                "bound": "hbm", "achieved": achieved, "peak": peak_gbs, "unit": "GB/s", "frac": achieved / peak_gbs,
+                "traffic": traffic, "traffic_source": traffic_src, "peak_source": peak_src,
+                "launches_per_step": kernel_launches, "gates_per_launch": num_gates / max(kernel_launches, 1),
+                "algorithmic_bytes_per_launch": bytes_step / max(kernel_launches, 1), "avg_launch_ms": ms_per_step / max(kernel_launches, 1),
+                "physical_gbs_estimate": physical, "physical_frac": physical / peak_gbs,
+                "fp64_tflops": fp64, "fp64_peak_tflops": FP64_PEAK_TFLOPS, "fp64_frac": fp64 / FP64_PEAK_TFLOPS,
+                "reading": "frac > 1 = fusion gain over one gate per HBM pass; the fused pass itself sits under BOTH roofs: physical_frac of HBM, fp64_frac of the FP64 pipe",
+                "sections": sections}
+    if nvlink:
+        roofline["nvlink"] = nvlink
+    del passes
+
+    secondary = None
+    if not args.no_secondary and not cfg3:
+        try:
+            secondary = secondary_configs(P, n_local, full=True)
+        except Exception as exc:                       # report, never fake
+            secondary = {"error": f"{type(exc).__name__}: {exc}"[:400]}
+        if secondary and f"cfg3_{31 + logw}q" in secondary and "ms_per_circuit" in secondary[f"cfg3_{31 + logw}q"]:
+            config[f"cfg3_{31 + logw}q_ms"] = secondary[f"cfg3_{31 + logw}q"]["ms_per_circuit"]
+        if secondary and world == 4 and "ms_per_circuit" in secondary.get("cfg3_34q", {}):
+            config["cfg3_34q_ms"] = secondary["cfg3_34q"]["ms_per_circuit"]
+
+    cpu_baseline = None
+    if rank == 0 and not args.no_cpu_baseline:
+        try:
+            ref = run_reference(n_local, 1, 1, args.cpu_sample, args.cpu_budget)
+            cpu_baseline = {k: ref[k] for k in ("value", "unit", "cores", "kind", "sample")}
+        except Exception as exc:                       # report, never fake
+            cpu_baseline = {"value": None, "unit": "gates/s", "cores": os.cpu_count(), "kind": "reference", "sample": f"failed: {exc}"[:300]}
+
+    if rank == 0:
+        detail = {"total_prob_after_run": total_prob, "circuit_gates_per_s": num_gates / (ms_per_step * 1e-3),
+                  "parallelism": f"state sharded over {world} GPUs on the top {logw} qubits" if world > 1 else "single GPU",
+                  "p2p_nvlink_kernels": bool(P.lib.qb_p2p_is_available()) if world > 1 else None,
+                  "timed_region": f"{args.steps} x (circuit + syncQuESTEnv), CUDA events, max over ranks"}
+        line = {"metric": METRIC, "value": world * num_gates / (ms_per_step * 1e-3), "unit": "gates/s", "n_gpus": world,
+                "steps": args.steps, "warmup": args.warmup, "ms_per_step": ms_per_step, "higher_is_better": True, "scaling": "weak",
+                "vs_baseline": None, "dtype": "f64", "data": "synthetic", "config": config, "roofline": roofline,
+                "cpu_baseline": cpu_baseline, "e2e": e2e, "gpu_launches": int(launches), "clocks": clocks, "detail": detail,
+                "secondary": secondary}
+        print(json.dumps(line))
+    P.barrier()
+    Q.finalizeQuESTEnv()
+    if P.dist:
+        P.dist.barrier()
+        P.dist.destroy_process_group()
+    return 0
+
+
 def main():
     ap = argparse.ArgumentParser()
     ap.add_argument("--gpus", type=int, default=1)
@@ -223,176 +607,32 @@ def main():
     ap.add_argument("--cpu-budget", type=float, default=25.0, help="seconds of CPU work per reference step")
     ap.add_argument("--no-cpu-baseline", action="store_true")
     ap.add_argument("--no-e2e", action="store_true")
-    ap.add_argument("--workload", default="cfg2", choices=["cfg2", "cfg3"], help="cfg3 (N>1 only): 100 random {H,Rx,CompMatr1,CNOT,CompMatr2} gates on initPlusState")
+    ap.add_argument("--no-secondary", action="store_true", help="skip the cfg 3/4/5 records")
+    ap.add_argument("--workload", default="cfg2", choices=["cfg2", "cfg3"], help="cfg3: 100 random {H,Rx,CompMatr1,CNOT,CompMatr2} gates on initPlusState")
     args = ap.parse_args()
 
     rank = int(os.environ.get("RANK", "0"))
     world = int(os.environ.get("WORLD_SIZE", "1"))
     local_rank = int(os.environ.get("LOCAL_RANK", "0"))
     n_local = args.qubits or 30
-    n = n_local + int(math.log2(max(1, world)))
-    config = {"workload": f"cfg2: {n}q fp64 statevector, applyFullQuantumFourierTransform + {NUM_DENSE} random dense 1/2-qubit gates",
-              "qubits": n, "amps_per_gpu": 1 << n_local, "gates_per_step": len(qft_stream(n)) + NUM_DENSE, "seed": SEED,
-              "l2_policy": "state (16 GiB per GPU) is far larger than L2; every gate streams it from HBM"}
-
-    if args.workload == "cfg3":
-        config.update({"workload": f"cfg3: {n}q fp64 statevector, initPlusState + 100 random gates from {{H, Rx, CompMatr1, CNOT, CompMatr2}}, targets uniform over all qubits",
-                       "gates_per_step": 100, "seed": 34008})
 
     if args.impl == "reference":
         if rank != 0:
             return 0
+        gpus = max(args.gpus, world)
+        config = build_config(n_local, gpus, args.workload, args.cpu_sample)
         ref = run_reference(n_local, args.steps, max(args.warmup, 1), args.cpu_sample, args.cpu_budget)
-        if world > 1 or args.gpus > 1:
-            config["reference_note"] = (f"the metric's unit is one gate applied to 2^{n_local} amplitudes; the CPU reference is timed on that unit "
-                                        f"({n_local}-qubit state, all host cores): it cannot hold the {n}-qubit sharded state")
-        line = {"impl": "reference", "metric": "30q fp64 gates/s", "value": ref["value"], "unit": "gates/s", "n_gpus": args.gpus,
+        line = {"impl": "reference", "metric": METRIC, "value": ref["value"], "unit": "gates/s", "n_gpus": gpus,
                 "steps": args.steps, "warmup": args.warmup, "ms_per_step": ref["ms_per_step"], "higher_is_better": True,
                 "scaling": "weak", "vs_baseline": None, "dtype": "f64", "data": "synthetic", "config": config,
                 "cpu_baseline": {k: ref[k] for k in ("value", "unit", "cores", "kind", "sample")},
                 "e2e": {"value": ref["value"], "unit": "gates/s", "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
-                "gpu_launches": 0}
+                "gpu_launches": 0,
+                "detail": {"note": "value = gates of the sample / CPU time: the reference applies one gate per pass over the 16 GiB state, so per-gate cost is "
+                                   "what the sample measures; ms_per_step is the time of the SAMPLE, not of the 680-gate step"}}
         print(json.dumps(line))
         return 0
-
-    import torch
-    from quest_b200 import capi
-
-    if not torch.cuda.is_available():
-        raise SystemExit("bench.py: no CUDA device; the quest_b200 backend has no CPU fallback")
-    torch.cuda.set_device(local_rank)
-    dist = None
-    if world > 1:
-        import torch.distributed as dist
-        dist.init_process_group("nccl", device_id=torch.device("cuda", local_rank))
-    capi.call("qb_bind_device", local_rank)
-
-    if world > 1:
-        from quest_b200 import dist_bench
-        return dist_bench.run(args, rank, world, local_rank, n, n_local, config, dist)
-
-    peaks = {}
-    try:
-        peaks = json.load(open(os.path.join(ROOT, "MEASURED_PEAKS.json")))
-    except Exception:
-        pass
-    peak_gbs, peak_src = (peaks["hbm_gbs"], "measured (MEASURED_PEAKS.json)") if "hbm_gbs" in peaks else (6650.0, "fallback (B200_PROFILING.md)")
-
-    qft, dense = qft_stream(n), dense_stream(n)
-    local_amps = 1 << n_local
-    bytes_qft = sum(algorithmic_bytes(op, local_amps) for op in qft)
-    bytes_dense = sum(algorithmic_bytes(op, local_amps) for op in dense)
-    num_gates = len(qft) + len(dense)
-
-    # Both timings drive QuEST's public API on the drop-in libQuEST.so (the call a user makes); the backend library
-    # underneath is the same shared object that `capi` binds, so qb_flush / qb_launch_count see the same queue.
-    from quest_b200 import quest_api as qa
-    Q = qa.QuEST(qa.B200_LIB)
-    Q.initCustomQuESTEnv(0, 1, 0)
-    qureg = Q.createCustomQureg(n, 0, 0, 1, 0)
-    assert qureg.isGpuAccelerated == 1
-    mats = [(op, Q.getCompMatr1(op[2]) if op[0] == "m1" else Q.getCompMatr2(op[3])) for op in dense]
-
-    def apply_dense():
-        for op, m in mats:
-            if op[0] == "m1":
-                Q.applyCompMatr1(qureg, op[1], m)
-            else:
-                Q.applyCompMatr2(qureg, op[1], op[2], m)
-
-    # ---------------- device-resident timing: state already in HBM, CUDA events on the backend's stream ----------------
-    # The backend defers work: fusable gates are queued until qb_flush, and uncontrolled SWAPs (the QFT's final layer)
-    # only relabel qubits until something needs the canonical order.  The timed region therefore ENDS with
-    # syncQuESTEnv(), which restores the canonical order and drains the stream, so nothing is left undone.
-    Q.initPlusState(qureg)
-    for _ in range(args.warmup):
-        Q.applyFullQuantumFourierTransform(qureg); capi.call("qb_flush")
-        apply_dense(); capi.call("qb_flush")
-    Q.syncQuESTEnv()
-    launches0 = capi.lib().qb_launch_count()
-    ev = [[torch.cuda.Event(enable_timing=True) for _ in range(3)] for _ in range(args.steps)]
-    ev_end = torch.cuda.Event(enable_timing=True)
-    sampler = ClockSampler(local_rank); sampler.start()
-    torch.cuda.synchronize()
-    dense_launches = 0
-    for k in range(args.steps):
-        ev[k][0].record()
-        Q.applyFullQuantumFourierTransform(qureg); capi.call("qb_flush")
-        ev[k][1].record()
-        l0 = capi.lib().qb_launch_count()
-        apply_dense(); capi.call("qb_flush")
-        dense_launches += capi.lib().qb_launch_count() - l0
-        ev[k][2].record()
-    Q.syncQuESTEnv()
-    ev_end.record()
-    torch.cuda.synchronize()
-    clocks = sampler.stop()
-    launches = capi.lib().qb_launch_count() - launches0
-    t_qft = sum(e[0].elapsed_time(e[1]) for e in ev) / args.steps          # ms
-    t_dense = sum(e[1].elapsed_time(e[2]) for e in ev) / args.steps
-    t_restore = ev[-1][2].elapsed_time(ev_end)                             # canonical qubit order restored once, after K steps
-    ms_per_step = ev[0][0].elapsed_time(ev_end) / args.steps
-    total_prob = Q.calcTotalProb(qureg)
-    config["timed_region"] = "K x (QFT + 200 dense gates) + syncQuESTEnv (restores canonical qubit order after lazily relabelled SWAPs)"
-    config["restore_ms_total"] = t_restore
-
-    # ---------------- e2e through the same API: + state initialisation, host matrices in, probability out ----------------
-    e2e = None
-    if not args.no_e2e:
-        h2d = sum(64 if op[0] == "m1" else 256 for op in dense) + 32 * sum(1 for op in qft if op[0] != "swap")
-
-        def e2e_step():
-            Q.initZeroState(qureg)
-            Q.applyFullQuantumFourierTransform(qureg)
-            apply_dense()
-            return Q.calcProbOfQubitOutcome(qureg, n - 1, 0)          # device->host read of the step's result
-
-        for _ in range(args.warmup):
-            e2e_step()
-        Q.syncQuESTEnv()
-        t0 = time.perf_counter()
-        for _ in range(args.steps):
-            prob = e2e_step()
-        Q.syncQuESTEnv()
-        dt = time.perf_counter() - t0
-        e2e = {"value": num_gates * args.steps / dt, "unit": "gates/s", "h2d_bytes_per_step": h2d, "d2h_bytes_per_step": 8,
-               "ms_per_step": 1e3 * dt / args.steps, "result_prob_of_top_qubit_0": prob,
-               "api": "initZeroState + applyFullQuantumFourierTransform + applyCompMatr1/2 x200 + calcProbOfQubitOutcome"}
-    Q.destroyQureg(qureg)
-
-    # the 200 dense gates run as `passes` kernel launches (tile-engine passes fusing several gates, or direct kernels);
-    # each launch streams the 2*16*2^n-byte state once, while its ALGORITHMIC bytes are the sum over the gates it applies
-    passes = dense_launches / args.steps
-    achieved = bytes_dense / (t_dense * 1e-3) / 1e9
-    physical = passes * 2 * AMP_BYTES * local_amps / (t_dense * 1e-3) / 1e9
-    roofline = {"kernel": "dense 1/2-qubit gate section: k_tile_pass (fused multi-gate passes) + direct k_tuple kernels",
-                "bound": "hbm", "achieved": achieved, "peak": peak_gbs,
-                "unit": "GB/s", "frac": achieved / peak_gbs,
-                # dram__bytes_read.sum + dram__bytes_write.sum per k_tile_pass launch, ncu --set full of this command
-                # (profiles/r1_final_launches_and_ncu.md): one read + one write of the state, whatever the number of fused gates
-                "traffic": 34.30e9 if n_local == 30 else None, "traffic_source": "ncu --set full, profiles/r1_final_launches_and_ncu.md",
-                "peak_source": peak_src,
-                "launches_per_step": passes, "gates_per_launch": len(dense) / max(passes, 1),
-                "algorithmic_bytes_per_launch": bytes_dense / max(passes, 1), "avg_launch_ms": t_dense / max(passes, 1),
-                "physical_gbs_estimate": physical, "physical_frac": physical / peak_gbs,
-                "qft_section": {"achieved_gbs": bytes_qft / (t_qft * 1e-3) / 1e9, "ms": t_qft, "gates": len(qft)},
-                "whole_step_gbs": (bytes_qft + bytes_dense) / (ms_per_step * 1e-3) / 1e9}
-    config["total_prob_after_run"] = total_prob
-
-    cpu_baseline = None
-    if not args.no_cpu_baseline:
-        try:
-            ref = run_reference(n_local, 1, 1, args.cpu_sample, args.cpu_budget)
-            cpu_baseline = {k: ref[k] for k in ("value", "unit", "cores", "kind", "sample")}
-        except Exception as exc:                       # report, never fake
-            cpu_baseline = {"value": None, "unit": "gates/s", "cores": os.cpu_count(), "kind": "reference", "sample": f"failed: {exc}"[:300]}
-
-    line = {"metric": "30q fp64 gates/s", "value": num_gates / (ms_per_step * 1e-3), "unit": "gates/s", "n_gpus": 1,
-            "steps": args.steps, "warmup": args.warmup, "ms_per_step": ms_per_step, "higher_is_better": True, "scaling": "weak",
-            "vs_baseline": None, "dtype": "f64", "data": "synthetic", "config": config, "roofline": roofline,
-            "cpu_baseline": cpu_baseline, "e2e": e2e, "gpu_launches": int(launches), "clocks": clocks}
-    print(json.dumps(line))
-    return 0
+    return run_product(args, rank, world, local_rank)
 
 
 if __name__ == "__main__":

@@ -80,9 +80,10 @@ int         qb_clear_cache(void);                        /* gpu_clearCache      
 size_t      qb_cache_bytes(void);                        /* gpu_getCacheMemoryInBytes  gpu_config.cpp:683 */
 unsigned long long qb_launch_count(void);                /* kernels launched by this library so far */
 int         qb_set_tile_engine(int enabled);             /* 1 (default): fused TMA tile passes (gate absorption + commuting re-order); 2: fused, program order; 0: direct kernels only */
-int         qb_selftest_bitins(const int* qubits, const int* states, int n, qb_index item, qb_index* out); /* host-only index-algebra check */
-int         qb_selftest_planner(int numQubits, int numOps, unsigned seed, int reorder, double* maxErr, int* numPasses, int* numRounds, int* numOpsPlanned); /* host-only: random gate list applied in program order vs in the tile planner's order (absorbed, merged, re-ordered) on a small host state */
-int         qb_selftest_tile_emulation(int numQubits, int numOps, unsigned seed, int reorder, double* maxErr, int* numTilePasses, int* numDirectOps); /* host-only: planner + emit_pass descriptors + the kernel's own round driver and gate bodies (compiled for the host) vs gate-by-gate application */
+/* cumulative statistics of the deferred-gate engine since load: out[0] fused tile passes launched, [1] register rounds
+ * in them, [2] gates executed inside tile passes, [3] gates run as direct kernels, [4] gates received by the queues,
+ * [5] FP64 fused multiply-adds executed for them (bench.py derives the FP64-pipe fraction of the roofline from it) */
+int         qb_tile_stats(double out[6]);
 
 /* ------------------------------------------------------------------------------------------
  * getters / setters                          (gpu_subroutines.hpp:24-36)

@@ -12,6 +12,9 @@ import re
 REPO_ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
 LIB_PATH = os.path.join(REPO_ROOT, "quest_b200", "lib", "libquest_b200.so")
 HEADER_PATH = os.path.join(REPO_ROOT, "include", "quest_b200.h")
+# test-only twin of the library carrying the host-side self-tests (include/quest_b200_selftest.h); never used by the product
+SELFTEST_LIB_PATH = os.path.join(REPO_ROOT, "quest_b200", "lib", "libquest_b200_selftest.so")
+SELFTEST_HEADER_PATH = os.path.join(REPO_ROOT, "include", "quest_b200_selftest.h")
 
 
 class qb_cplx(C.Structure):
@@ -75,6 +78,22 @@ def lib():
             fn = getattr(_lib, name)
             fn.restype, fn.argtypes = res, args
     return _lib
+
+
+_selftest_lib = None
+
+
+def selftest_lib():
+    """the -DQB_SELFTEST build of the library (host-only planner / index-algebra self-tests for the CPU test-suite)"""
+    global _selftest_lib
+    if _selftest_lib is None:
+        if not os.path.exists(SELFTEST_LIB_PATH):
+            raise QbError(f"{SELFTEST_LIB_PATH} not built: run `make selftest`")
+        _selftest_lib = C.CDLL(SELFTEST_LIB_PATH, mode=C.RTLD_LOCAL)
+        for name, (res, args) in prototypes(SELFTEST_HEADER_PATH).items():
+            fn = getattr(_selftest_lib, name)
+            fn.restype, fn.argtypes = res, args
+    return _selftest_lib
 
 
 def check(status, what=""):

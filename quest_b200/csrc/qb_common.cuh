@@ -44,6 +44,7 @@ int  qb_ensure_ready();   // binds device 0 lazily, allocates scratch; returns 0
 #define QB_CUDA(call) do { cudaError_t e__ = (call); if (e__ != cudaSuccess) \
     return qb_set_error((int)e__, #call, __FILE__, __LINE__); } while (0)
 int  qb_flush_internal();  // qb_tile.cu: run every deferred (queued) gate now
+void qb_tile_forget(const void* amps);   // qb_tile.cu: drop the (already flushed) queue of a state that is being freed
 // every entry point first makes the device ready and drains the deferred-gate queue; the fusable gate entry points
 // use QB_READY_NOFLUSH and either append to the queue or flush explicitly before running a direct kernel
 #define QB_READY_NOFLUSH() do { int r__ = qb_ensure_ready(); if (r__) return r__; } while (0)

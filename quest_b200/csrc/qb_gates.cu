@@ -452,7 +452,6 @@ int qb_statevec_anyCtrlAnyTargDenseMatr_sub(const qb_state* q, const int* ctrls,
     QB_READY(); QB_CHECK_STATE(q); QB_CHECK_SUFFIX(ctrls, nc, q); QB_CHECK_SUFFIX(targs, nt, q);
     QB_REQUIRE(nt >= 1 && devMatr, "denseK: need >= 1 target and a device matrix");
     QB_REQUIRE(nc + nt <= q->logNumAmpsPerNode, "denseK: more qubits than the local state holds");
-    if (qb_tile_try_denseK(q, ctrls, cs, nc, targs, nt, devMatr, conj)) return qb_tile_status();
     int z[QB_MAX_QUBITS] = {0};
     BitIns ins = qb_make_ins(ctrls, cs, nc, targs, z, nt);
     BitList tl = qb_make_list(targs, nt);

@@ -3,6 +3,9 @@
 // sync :382, alloc :399-431, copies :449-623, cache :635-687) behind the C ABI.
 #include "qb_common.cuh"
 #include "qb_reduce.cuh"
+#ifdef QB_SELFTEST
+#include "../../include/quest_b200_selftest.h"
+#endif
 #include <string.h>
 #include <string>
 #include <algorithm>
@@ -199,6 +202,7 @@ int qb_free(qb_cplx* p) {
     if (!p) return 0;
     QB_READY();
     QB_CUDA(cudaStreamSynchronize(g_qb.stream));
+    qb_tile_forget(p);
     { int r = qb_p2p_note_free(p); if (r) return r; }
     QB_CUDA(cudaFree(p));
     return 0;
@@ -264,6 +268,7 @@ int qb_statevec_getAmp_sub(const qb_state* q, qb_index ind, qb_cplx* out) {
     return qb_copy_d2h(out, q->amps + ind, 1);
 }
 
+#ifdef QB_SELFTEST
 // host-side self test of the index algebra used by every kernel: BitIns against the literal
 // one-bit-at-a-time definition (core/bitwise.hpp:99-105,164-171,206-210). Returns #mismatches.
 int qb_selftest_bitins(const int* qubits, const int* states, int n, qb_index item, qb_index* out) {
@@ -278,5 +283,7 @@ int qb_selftest_bitins(const int* qubits, const int* states, int n, qb_index ite
     if (out) *out = got;
     return got != want;
 }
+
+#endif  // QB_SELFTEST
 
 } // extern "C"

@@ -30,6 +30,9 @@
 #include "qb_common.cuh"
 #include "qb_kernels.cuh"
 #include "qb_tile.cuh"
+#ifdef QB_SELFTEST
+#include "../../include/quest_b200_selftest.h"
+#endif
 #include <math.h>
 #include <stddef.h>
 #include <string.h>
@@ -70,12 +73,20 @@ struct QOp {
     qindex algBytes;
 };
 
-static std::vector<QOp> s_queue;
-static qb_state s_qstate;                      // identity of the state the queue refers to
-static bool s_qvalid = false;
+// One deferred queue PER STATE (keyed by the amplitude pointer): programs that alternate gates between several Quregs
+// -- the reference's own psi / rho co-evolution test, tests/integration/densitymatrix.cpp:68-163 -- keep fusing on each
+// of them; with a single global queue every switch would flush and the engine would degrade to one gate per pass.
+// Queues of different states are independent (disjoint memory; a queue whose range overlaps a newcomer's is flushed
+// first), so "flush" may run them in any order: it runs them in creation order.
+struct StateQueue { qb_state st; std::vector<QOp> ops; };
+#define MAX_STATE_QUEUES 8
+static std::vector<StateQueue> s_queues;
 static int s_status = 0;
 static bool s_inFlush = false;
 static unsigned long long s_flushEpoch = 0;       // bumped whenever a non-empty queue is executed
+// cumulative execution statistics (qb_tile_stats): what the planner made of the gates it was given
+static unsigned long long s_statPasses = 0, s_statRounds = 0, s_statTileOps = 0, s_statDirectOps = 0, s_statQueuedGates = 0;
+static double s_statFmaAmps = 0;                   // FP64 fused multiply-adds issued per pass, summed: ops x amplitudes x FMA per amplitude
 
 // device-side op, in tile coordinates
 struct TileOp {
@@ -139,6 +150,26 @@ __device__ __forceinline__ void tma_commit() { asm volatile("cp.async.bulk.commi
 template <int N> __device__ __forceinline__ void tma_wait_read() { asm volatile("cp.async.bulk.wait_group.read %0;" :: "n"(N) : "memory"); }
 template <int N> __device__ __forceinline__ void tma_wait_all() { asm volatile("cp.async.bulk.wait_group %0;" :: "n"(N) : "memory"); }
 __device__ __forceinline__ void fence_async_smem() { asm volatile("fence.proxy.async.shared::cta;" ::: "memory"); }
+
+// optional cycle accounting of the compute warpgroups (probe builds only: -DQB_TILE_TIMING, tools/tile_timing_probe.py)
+#ifdef QB_TILE_TIMING
+#define TT_SLOTS 12
+__device__ unsigned long long g_tileTiming[TT_SLOTS];
+#endif
+#if defined(QB_TILE_TIMING) && defined(__CUDA_ARCH__)
+__device__ __forceinline__ unsigned long long tt_now() { unsigned long long t; asm volatile("mov.u64 %0, %clock64;" : "=l"(t) :: "memory"); return t; }
+#define TT_DECL unsigned long long tt_prev = tt_now(), tt_acc[TT_SLOTS] = {0}
+#define TT_MARK(slot) do { unsigned long long n_ = tt_now(); tt_acc[slot] += n_ - tt_prev; tt_prev = n_; } while (0)
+#define TT_ARGS , unsigned long long& tt_prev, unsigned long long (&tt_acc)[TT_SLOTS]
+#define TT_PASS , tt_prev, tt_acc
+#define TT_FLUSH do { if ((threadIdx.x & 127) == 0) for (int i_ = 0; i_ < TT_SLOTS; i_++) atomicAdd(&g_tileTiming[i_], tt_acc[i_]); } while (0)
+#else
+#define TT_DECL
+#define TT_MARK(slot)
+#define TT_ARGS
+#define TT_PASS
+#define TT_FLUSH
+#endif
 
 // the gate bodies and the round driver below are compiled for the device (k_tile_pass) AND for the host, where the
 // CPU self-test qb_selftest_tile_emulation runs the very same code on the descriptors emit_pass produced
@@ -266,7 +297,7 @@ QB_HD void reg_hstar_bit(cplx (&v)[RAMPS], cplx ebs, const cplx* __restrict__ mu
 // `active` (bit i <-> op i of the pass) holds the tile-uniform tests: external controls, external star centres.
 // ------------------------------------------------------------------------------------------
 QB_HD void reg_round(cplx* __restrict__ t, const RoundHdr& rd, const TileOp* __restrict__ ops, qindex base,
-                                          unsigned long long active0, const StarTab* __restrict__ tabs, const cplx* __restrict__ starF, int wtid) {
+                                          unsigned long long active0, const StarTab* __restrict__ tabs, const cplx* __restrict__ starF, int wtid TT_ARGS) {
   for (int it = 0; it < WG_ITERS; it++) {
     const int tid = wtid + it * WG_THREADS;
     unsigned long long active = active0;
@@ -289,6 +320,7 @@ QB_HD void reg_round(cplx* __restrict__ t, const RoundHdr& rd, const TileOp* __r
     cplx v[RAMPS];
 #pragma unroll
     for (int u = 0; u < RAMPS; u++) v[u] = t[jb | OFF(u)];
+    TT_MARK(4);      // address arithmetic + issue of the 16 shared-memory loads
 
     for (int o = 0; o < num; o++, op++, active >>= 1) {
         int4 dn = d; cplx na = pa, nb = pb, nc_ = pc, nd = pd;
@@ -360,8 +392,10 @@ QB_HD void reg_round(cplx* __restrict__ t, const RoundHdr& rd, const TileOp* __r
         }
         d = dn; pa = na; pb = nb; pc = nc_; pd = nd;
     }
+    TT_MARK(5);      // gates (includes waiting for the loads to land)
 #pragma unroll
     for (int u = 0; u < RAMPS; u++) t[jb | OFF(u)] = v[u];
+    TT_MARK(6);      // 16 shared-memory stores
   }
 #undef PREFETCH
 #undef OFF
@@ -460,6 +494,7 @@ __global__ void __launch_bounds__(TILE_BLOCK, 1) k_tile_pass(cplx* __restrict__ 
     // two warpgroups, each taking every other tile of this CTA and running it alone (own named barrier): their phases
     // drift apart, so one group's shared-memory traffic, barriers and gate dispatch overlap the other's FP64 work
     const int wg = tid / WG_THREADS, wtid = tid % WG_THREADS;
+    TT_DECL;
     for (qindex k = wg; k < myCount; k += 2) {
         const int s = (int)(k % TILE_STAGES);
         const unsigned parity = (unsigned)((k / TILE_STAGES) & 1);
@@ -491,25 +526,42 @@ __global__ void __launch_bounds__(TILE_BLOCK, 1) k_tile_pass(cplx* __restrict__ 
         // from the preceding one, so this group must not poll `full` for tile k while the barrier may still be in the
         // phase of tile k - 3: first see that tile consumed (its `done` phase is unambiguous here -- the phase before it
         // was completed by this very group), after which `full` can only be in tile k's phase or past it.
+        TT_MARK(0);      // per-tile prologue (star factors, tile-uniform tests)
         if (k >= TILE_STAGES) mbar_wait(&done[s], (unsigned)(((k - TILE_STAGES) / TILE_STAGES) & 1));
+        TT_MARK(1);      // waiting for the stage's previous tile to be consumed
         mbar_wait(&full[s], parity);
+        TT_MARK(2);      // waiting for the tile to land (TMA load)
         wg_sync(wg);
+        TT_MARK(3);      // warpgroup barrier at tile start
 
         for (int r = 0; r < numRounds; r++) {
             const RoundHdr& rd = rounds[r];
             if (rd.kind == ROUND_REG) {
-                reg_round(t, rd, ops, base, active, tabs, sf, wtid);
+                reg_round(t, rd, ops, base, active, tabs, sf, wtid TT_PASS);
             } else {
                 if ((active >> rd.opBase) & 1) smem_pauli(t, ops[rd.opBase], base, wtid);
+                TT_MARK(7);
             }
-            if (r + 1 < numRounds) wg_sync(wg);
+            if (r + 1 < numRounds) { wg_sync(wg); TT_MARK(8); }     // warpgroup barrier between rounds
         }
         // hand the tile to the copy warp: make this warp's shared-memory writes visible to the async proxy, then arrive
         fence_async_smem();
         __syncwarp();
         if (lane == 0) mbar_arrive(&done[s]);
+        TT_MARK(9);      // fence + arrive
     }
+    TT_FLUSH;
 }
+
+#ifdef QB_TILE_TIMING
+extern "C" int qb_tile_timing_read(unsigned long long* out12, int reset) {
+    unsigned long long z[TT_SLOTS] = {0};
+    cudaDeviceSynchronize();
+    if (out12) cudaMemcpyFromSymbol(out12, g_tileTiming, sizeof z);
+    if (reset) cudaMemcpyToSymbol(g_tileTiming, z, sizeof z);
+    return 0;
+}
+#endif
 
 // ------------------------------------------------------------------------------------------
 // host: planner
@@ -922,12 +974,37 @@ static void plan_passes(std::vector<QOp>& ops, bool reorder, std::vector<QOp>& m
 
 }
 
+// FP64 fused multiply-adds per touched amplitude of each op kind (complex arithmetic written out: cmul = 4, cfma = 4)
+static double fma_per_amp(const QOp& o) {
+    double f;
+    switch (o.kind) {
+    case OP_DENSE1: f = 8; break;
+    case OP_DENSE2: f = 16; break;
+    case OP_PAULI: f = 8; break;
+    case OP_SWAP: f = 0; break;
+    case OP_HSTAR: f = 7; break;
+    default: f = 4; break;                    // diagonal / parity / star: one complex multiply
+    }
+    return f / (double)(1ULL << __builtin_popcountll(o.ctrlMask));
+}
+
+static int flush_one(StateQueue& sq);
+
 static int flush_queue() {
-    if (s_queue.empty() || s_inFlush) return 0;
+    if (s_queues.empty() || s_inFlush) return 0;
+    int rc = 0;
+    std::vector<StateQueue> all; all.swap(s_queues);
+    for (StateQueue& sq : all) { int r = flush_one(sq); if (r && !rc) rc = r; }
+    return rc;
+}
+
+static int flush_one(StateQueue& sq) {
+    if (sq.ops.empty()) return 0;
     s_inFlush = true;
     s_flushEpoch++;
-    std::vector<QOp> ops; ops.swap(s_queue);
-    qb_state q = s_qstate; s_qvalid = false;
+    std::vector<QOp> ops; ops.swap(sq.ops);
+    qb_state q = sq.st;
+    s_statQueuedGates += ops.size();
     const int n = q.logNumAmpsPerNode;
     int rc = 0;
     const bool reorder = g_qb.tileEngine != 2;
@@ -940,7 +1017,10 @@ static int flush_queue() {
     for (auto& p : passes) {
         bool direct = (p.high == ~0ULL) || (p.opIdx.size() == 1 && merged[p.opIdx[0]].kind != OP_STAR && merged[p.opIdx[0]].kind != OP_HSTAR) || n < TILE_BITS;
         if (direct) { for (int idx : p.opIdx) { passKind.push_back(-1); passArg.push_back(idx); } }
-        else { passKind.push_back((int)E.hdrs.size()); passArg.push_back(0); emit_pass(&q, merged, p, E, reorder); }
+        else {
+            passKind.push_back((int)E.hdrs.size()); passArg.push_back(0); emit_pass(&q, merged, p, E, reorder);
+            for (int idx : p.opIdx) s_statFmaAmps += fma_per_amp(merged[idx]) * (double)q.numAmpsPerNode;
+        }
     }
     const size_t bh = E.hdrs.size() * sizeof(PassHdr), br = E.rounds.size() * sizeof(RoundHdr),
                  bo = E.ops.size() * sizeof(TileOp), bt = E.tabs.size() * sizeof(StarTab);
@@ -968,8 +1048,9 @@ static int flush_queue() {
         attrSet = true;
     }
     for (size_t i = 0; i < passKind.size() && !rc; i++) {
-        if (passKind[i] < 0) { rc = run_direct(&q, merged[passArg[i]]); continue; }
+        if (passKind[i] < 0) { rc = run_direct(&q, merged[passArg[i]]); s_statDirectOps++; s_statFmaAmps += fma_per_amp(merged[passArg[i]]) * (double)q.numAmpsPerNode; continue; }
         const int hi = passKind[i];
+        s_statPasses++; s_statRounds += E.hdrs[hi].numRounds; s_statTileOps += E.hdrs[hi].numOps;
         const PassHdr* dh = (const PassHdr*)s_devDesc + hi;
         const RoundHdr* dr = (const RoundHdr*)(s_devDesc + bh) + E.roundBase[hi];
         const TileOp* dops = (const TileOp*)(s_devDesc + bh + br) + E.opBase[hi];
@@ -990,15 +1071,36 @@ int qb_flush_internal() { return flush_queue(); }
 // what the deferred queue of this state still holds: number of gates, and every suffix qubit any of them involves
 // (targets, controls, diagonal / Z sites).  The sharding layer uses it to run a half-shard swap AHEAD of the queued
 // gates when they commute with it (no queued gate touches the swapped suffix qubit), instead of flushing the queue.
+static StateQueue* find_queue(const qb_state* q) {
+    for (StateQueue& sq : s_queues) if (sq.st.amps == q->amps) return &sq;
+    return nullptr;
+}
+
 extern "C" int qb_queue_info(const qb_state* q, unsigned long long* touchedSuffixMask, unsigned long long* flushEpoch) {
     unsigned long long mask = 0; int len = 0;
-    if (q && s_qvalid && s_qstate.amps == q->amps) {
-        len = (int)s_queue.size();
-        for (const QOp& o : s_queue) mask |= nonDiagTargets(o) | diagQubits(o);
+    if (q) if (StateQueue* sq = find_queue(q)) {
+        len = (int)sq->ops.size();
+        for (const QOp& o : sq->ops) mask |= nonDiagTargets(o) | diagQubits(o);
     }
     if (touchedSuffixMask) *touchedSuffixMask = mask;
     if (flushEpoch) *flushEpoch = s_flushEpoch;
     return len;
+}
+
+// cumulative planner / execution statistics since the library was loaded:
+// out[0] tile passes launched, [1] rounds in them, [2] ops executed inside tile passes, [3] ops run as direct kernels,
+// [4] gates received by the queue, [5] FP64 fused multiply-adds executed for them (thread-level count)
+extern "C" int qb_tile_stats(double out[6]) {
+    if (!out) return -1;
+    out[0] = (double)s_statPasses; out[1] = (double)s_statRounds; out[2] = (double)s_statTileOps; out[3] = (double)s_statDirectOps;
+    out[4] = (double)s_statQueuedGates; out[5] = s_statFmaAmps;
+    return 0;
+}
+
+// called by qb_free: whatever is still queued for memory about to be released must run first (QB_READY in qb_free
+// has already flushed); nothing may keep referring to the pointer
+void qb_tile_forget(const void* amps) {
+    for (size_t i = 0; i < s_queues.size(); i++) if (s_queues[i].st.amps == amps) { s_queues.erase(s_queues.begin() + i); return; }
 }
 
 // ------------------------------------------------------------------------------------------
@@ -1008,15 +1110,28 @@ static bool can_fuse(const qb_state* q) {
     return g_qb.tileEngine && !s_inFlush && q->logNumAmpsPerNode >= FUSE_MIN_LOG_AMPS && q->logNumAmpsPerNode <= 36;
 }
 
-static bool same_state(const qb_state* q) {
-    return s_qvalid && s_qstate.amps == q->amps && s_qstate.numAmpsPerNode == q->numAmpsPerNode && s_qstate.rank == q->rank;
-}
-
 static int enqueue(const qb_state* q, QOp& o) {
-    if (!same_state(q)) { int r = flush_queue(); if (r) { s_status = r; return 1; } s_qstate = *q; s_qvalid = true; }
-    s_queue.push_back(o);
     s_status = 0;
-    if (s_queue.size() >= QUEUE_MAX) s_status = flush_queue();
+    StateQueue* sq = find_queue(q);
+    if (sq && (sq->st.numAmpsPerNode != q->numAmpsPerNode || sq->st.rank != q->rank || sq->st.logNumAmpsPerNode != q->logNumAmpsPerNode)) {
+        int r = flush_one(*sq); if (r) { s_status = r; return 1; }      // same memory seen through a different view
+        sq->st = *q;
+    }
+    if (!sq) {
+        // a newcomer whose memory overlaps a queued state's (a view into the middle of another allocation) must not
+        // overtake it; and the table is kept small: the oldest queue is run when it is full
+        const char* lo = (const char*)q->amps; const char* hi = lo + (size_t)q->numAmpsPerNode * sizeof(cplx);
+        for (size_t i = 0; i < s_queues.size(); ) {
+            const char* a = (const char*)s_queues[i].st.amps; const char* b = a + (size_t)s_queues[i].st.numAmpsPerNode * sizeof(cplx);
+            if (a < hi && lo < b) { int r = flush_one(s_queues[i]); s_queues.erase(s_queues.begin() + i); if (r) { s_status = r; return 1; } }
+            else i++;
+        }
+        if (s_queues.size() >= MAX_STATE_QUEUES) { int r = flush_one(s_queues[0]); s_queues.erase(s_queues.begin()); if (r) { s_status = r; return 1; } }
+        s_queues.push_back(StateQueue{*q, {}});
+        sq = &s_queues.back();
+    }
+    sq->ops.push_back(o);
+    if (sq->ops.size() >= QUEUE_MAX) s_status = flush_one(*sq);
     return 1;
 }
 
@@ -1042,8 +1157,6 @@ int qb_tile_try_dense(const qb_state* q, const int* ctrls, const int* cs, int nc
     for (int i = 0; i < (nt == 1 ? 4 : 16); i++) o.m[i] = mk(m[i]);
     return enqueue(q, o);
 }
-
-int qb_tile_try_denseK(const qb_state*, const int*, const int*, int, const int*, int, const qb_cplx*, int) { return 0; }
 
 int qb_tile_try_diag(const qb_state* q, const int* ctrls, const int* cs, int nc, const int* targs, int nt, const qb_cplx* e) {
     if (!can_fuse(q) || nt > 2) return 0;
@@ -1137,6 +1250,7 @@ static int run_direct(const qb_state* q, const QOp& o) {
     return qb_set_error(-1, "tile engine: unknown op", __FILE__, __LINE__);
 }
 
+#if defined(QB_SELFTEST) && !defined(QB_TILE_TIMING)
 // ------------------------------------------------------------------------------------------
 // host-only self-test of the planner (no CUDA): a random gate list is applied to a small random state vector twice --
 // gate by gate in program order, and in the planner's order (after gate absorption, star merging, Hadamard+star
@@ -1366,3 +1480,4 @@ extern "C" int qb_selftest_tile_emulation(int numQubits, int numOps, unsigned se
     if (numDirectOps) *numDirectOps = directOps;
     return 0;
 }
+#endif  // QB_SELFTEST

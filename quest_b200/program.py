@@ -9,8 +9,9 @@ program = {
   "quregs": {"psi": {"n": 6, "dm": 0, "init": "debug" | "zero" | "plus" | "blank" | ["classical", k],
                      "custom": [useDistrib, useGpuAccel, useMultithread]  (optional createCustomQureg)}},
   "ops": [ ["applyCompMatr1", "psi", 3, {"m1": [[re,im]*4]}], ["calcTotalProb", "psi"], ... ],
-  "dump": ["psi"]                        # quregs whose full amplitudes are returned
-}
+  "dump": ["psi"],                       # quregs whose full amplitudes are returned
+  "dump_windows": {"rho": [[start, width], ...]}   # (optional) slices of the local flat amplitude array, returned as
+}                                                  # dumps["rho@start"]: for states too large to dump whole
 Special argument encodings (everything else is passed through as int/float/list-of-int):
   "name"                -> the Qureg of that name (only where the API takes a Qureg)
   {"m1": M} {"m2": M}   -> CompMatr1 / CompMatr2 (by value);   {"m": M} -> heap CompMatr (created, synced, destroyed)
@@ -20,6 +21,7 @@ Special argument encodings (everything else is passed through as int/float/list-
   {"c": [re, im]}       -> qcomp by value
   {"out_reals": k}      -> a qreal[k] output array (returned as the op's result)
   {"amps": [[re,im]..]} -> a host qcomp array passed by pointer (setQuregAmps, setDensityQuregFlatAmps ...)
+  {"out_amps": k}       -> a qcomp[k] output array passed by pointer (getQuregAmps); returned as a complex ndarray
 Complex matrices are nested lists of [re, im] pairs (or anything np.asarray(...).view understands).
 """
 import ctypes as C
@@ -81,6 +83,8 @@ class _Interp:
                 self.cleanup.append(("destroyPauliStrSum", obj)); return obj
             if k == "amps":
                 arr = np.ascontiguousarray(dec_mat(v), dtype=np.complex128); self.keep.append(arr); return arr.ctypes.data
+            if k == "out_amps":
+                arr = np.zeros(int(v), dtype=np.complex128); self.outarr = arr; return arr.ctypes.data
             if k == "out_reals":
                 arr = (C.c_double * int(v))(); self.outarr = arr; return arr
             raise ValueError(f"unknown argument encoding {k}")
@@ -115,7 +119,9 @@ class _Interp:
             self.keep, self.outarr = [], None
             cargs = [self.conv(a) for a in args]
             out = getattr(Q.lib, name)(*cargs)
-            if self.outarr is not None:
+            if isinstance(self.outarr, np.ndarray):
+                out = self.outarr
+            elif self.outarr is not None:
                 out = list(self.outarr)
             elif isinstance(out, qa.qcomp):
                 out = [out.re, out.im]
@@ -132,6 +138,13 @@ class _Interp:
         for name in prog.get("dump", []):
             q = self.quregs[name]
             dumps[name] = Q.getLocalAmps(q) if (q.isDensityMatrix or q.isDistributed) else Q.getAmps(q)
+        for name, wins in prog.get("dump_windows", {}).items():
+            q = self.quregs[name]
+            if q.isGpuAccelerated:
+                Q.lib.syncQuregFromGpu(q)
+            flat = Q._view(q.cpuAmps, q.numAmpsPerNode)
+            for start, width in wins:
+                dumps[f"{name}@{int(start)}"] = np.array(flat[int(start):int(start) + int(width)])
         info = {name: {f: getattr(q, f) for f in ("isGpuAccelerated", "isDistributed", "isMultithreaded", "rank",
                                                    "numNodes", "numAmpsPerNode")} for name, q in self.quregs.items()}
         for q in self.quregs.values():

@@ -39,6 +39,8 @@ def rel_l2(a, b):
 def flatten_result(r):
     if r is None or isinstance(r, str):
         return None
+    if isinstance(r, np.ndarray) and np.iscomplexobj(r):
+        return np.ascontiguousarray(r).view(np.float64).ravel()
     return np.asarray(r, dtype=np.float64).ravel()
 
 

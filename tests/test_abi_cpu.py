@@ -18,6 +18,10 @@ def test_library_exports_every_declared_symbol():
     missing = [n for n in names if not hasattr(lib, n)]
     assert not missing, f"declared in quest_b200.h but not exported: {missing}"
     assert lib.qb_abi_version() == 1
+    # the host-side self-tests are compiled OUT of the product library (they live in the -DQB_SELFTEST twin)
+    assert not any(hasattr(lib, n) for n in ("qb_selftest_planner", "qb_selftest_tile_emulation", "qb_selftest_bitins"))
+    st = capi.selftest_lib()
+    assert all(hasattr(st, n) for n in capi.prototypes(capi.SELFTEST_HEADER_PATH))
 
 
 def test_header_prototypes_parse():
@@ -43,7 +47,7 @@ def test_dropin_library_exports_reference_api():
 
 def test_bit_insertion_matches_reference_definition():
     """BitIns (<=4 scalar inserts, else the branch-free expand) == insertBitsWithMaskedValues (bitwise.hpp:206)"""
-    lib = capi.lib()
+    lib = capi.selftest_lib()
     rng = np.random.default_rng(3)
     out = C.c_longlong()
     for _ in range(3000):
@@ -77,7 +81,7 @@ def test_tile_planner_preserves_the_circuit(n, reorder):
     """host logic of the tile engine (quest_b200/csrc/qb_tile.cu: gate absorption, phase-star merging, Hadamard+star
     fusion, commuting first-fit grouping into passes and rounds): a random gate list applied in the planner's order to a
     small host state must equal gate-by-gate application in program order.  No GPU involved."""
-    lib = capi.lib()
+    lib = capi.selftest_lib()
     err, passes, rounds, planned = C.c_double(), C.c_int(), C.c_int(), C.c_int()
     for seed in range(8):
         num_ops = 200
@@ -124,7 +128,7 @@ def test_tile_kernel_emulation_on_host(n, reorder):
     bits, dispatch codes, phase-star tables) -> the kernel's own round driver and gate bodies, which are compiled for the
     host as well as for the device (same source, quest_b200/csrc/qb_tile.cu) -> compared with plain gate-by-gate
     application.  Only the TMA / mbarrier tile pipeline itself is left to the GPU tests."""
-    lib = capi.lib()
+    lib = capi.selftest_lib()
     err, tile_passes, direct_ops = C.c_double(), C.c_int(), C.c_int()
     total_tile_passes = 0
     for seed in range(6):

@@ -2,7 +2,8 @@
 quest_b200/lib/libQuEST.so (reference host layers + our sm_100a backend, GPU-accelerated Quregs only) and are
 compared with (a) the committed golden outputs of the unmodified reference CPU library and (b) the live
 reference library oracle/_ref/libQuEST.so at larger sizes.  fp64 tolerance 1e-12 relative L2; measurement
-outcomes bit-exact."""
+outcomes bit-exact.  The BASELINE configurations at their FULL sizes are compared with the reference in
+tests/test_fullsize_gpu.py."""
 import os
 
 import numpy as np
@@ -86,38 +87,7 @@ def test_qft_known_answer_26q():
     assert abs(out["results"][1] - 1) < 1e-12 and abs(out["results"][2] - 0.5) < 1e-12
 
 
-def test_cfg2_full_size_roundtrip_30q():
-    """BASELINE cfg 2 at its FULL size (30 qubits, 16 GiB), where no CPU replay is affordable: size-independent properties.
-    QFT|0..0> = |+>^30; the 200 random dense gates followed by their inverses in reverse order must return to it.  |+>^n is
-    the unique state with <X_q> = 1 for every q, so 30 one-qubit expectations pin the whole final state (up to a global
-    phase); a few probabilities and Z-expectations cross-check.  The deferred queue, gate absorption, re-ordering and the
-    lazily relabelled QFT swaps are all exercised at the size the bench runs."""
-    n = 30
-    rng = np.random.default_rng(20302)
-    fwd = []
-    for _ in range(200):
-        if rng.integers(2):
-            fwd.append(("m1", [int(rng.integers(n))], P.rand_unitary(rng, 2)))
-        else:
-            fwd.append(("m2", P._pick(rng, n, 2), P.rand_unitary(rng, 4)))
-    ops = [["applyFullQuantumFourierTransform", "psi"]]
-    for kind, t, u in fwd + [(k, t, u.conj().T) for k, t, u in reversed(fwd)]:
-        if kind == "m1":
-            ops.append(["applyCompMatr1", "psi", t[0], {"m1": P.enc_mat(u)}])
-        else:
-            ops.append(["applyCompMatr2", "psi", t[0], t[1], {"m2": P.enc_mat(u)}])
-    first_check = len(ops)
-    ops.append(["calcTotalProb", "psi"])
-    for q in range(n):
-        ops.append(["calcExpecPauliStr", "psi", {"pauli": ["X", [q]]}])
-    ops.append(["calcExpecPauliStr", "psi", {"pauli": ["XXX", [0, 13, 29]]}])
-    ops.append(["calcExpecPauliStr", "psi", {"pauli": ["Z", [7]]}])
-    ops.append(["calcExpecPauliStr", "psi", {"pauli": ["ZY", [3, 28]]}])
-    ops.append(["calcProbOfMultiQubitOutcome", "psi", [0, 14, 29], [1, 0, 1], 3])
-    prog = {"quregs": {"psi": {"n": n, "init": "zero"}}, "ops": ops, "dump": []}
-    res = H.run_programs("b200", [prog])[0]["results"][first_check:]
-    assert abs(res[0] - 1) < 1e-11, f"norm after 880 gates: {res[0]}"
-    worst = max(abs(x - 1) for x in res[1:n + 1])
-    assert worst < 1e-11, f"<X_q> deviates from 1 by {worst:.3e}: the circuit and its inverse do not cancel"
-    assert abs(res[n + 1] - 1) < 1e-11 and abs(res[n + 2]) < 1e-11 and abs(res[n + 3]) < 1e-11
-    assert abs(res[n + 4] - 0.125) < 1e-12
+def test_live_interleaved_quregs_coevolution():
+    """the reference's psi / rho co-evolution pattern (tests/integration/densitymatrix.cpp:68-163): identical gates applied
+    alternately to a statevector, a density matrix and a third register; the backend keeps one deferred queue per state"""
+    _live([P.coevolution_program(9, 4301), P.coevolution_program(13, 4302, num_ops=40)])

@@ -636,3 +636,74 @@ def test_fused_qft_matches_gate_by_gate(n):
     assert rel_l2(results[1], want) <= 1e-11, "gate-by-gate QFT disagrees with the DFT"
     assert rel_l2(results[0], want) <= 1e-11, "fused QFT disagrees with the DFT"
     assert rel_l2(results[0], results[1]) <= TOL * 5
+
+
+@pytest.mark.parametrize("n", [3, 9, 16, 20])
+def test_pauli_expectation_with_buffer_partner_subB(n):
+    """calcExpecPauliStr_subB / Batch_subB (gpu_subroutines.cpp:1698): the partner amplitude a_j comes from the
+    communication buffer (what a full exchange with rank ^ prefixXY leaves there), single GPU, rank emulated"""
+    rng = np.random.default_rng(2100 + n)
+    outc = capi.qb_cplx()
+    for rank, logNodes in ((0, 1), (1, 1), (2, 2), (5, 3)):
+        st = rand_sv(rng, n + logNodes, rank, logNodes, buffer=True); dev = Dev(st)
+        terms, masks = [], []
+        for _ in range(9):
+            k = int(rng.integers(1, min(n, 5) + 1)); qs = pick(rng, n, k); chars = rng.choice(list("XYZ"), size=k)
+            x = [q for ch, q in zip(chars, qs) if ch == "X"]; y = [q for ch, q in zip(chars, qs) if ch == "Y"]
+            z = [q for ch, q in zip(chars, qs) if ch == "Z"]
+            capi.call("qb_statevec_calcExpecPauliStr_subB", dev.ref, capi.ints(x), len(x), capi.ints(y), len(y), capi.ints(z), len(z), C.byref(outc))
+            want = qo.statevec_calcExpecPauliStr_subB(st, x, y, z)
+            assert abs(complex(outc.re, outc.im) - want) <= TOL, f"subB n={n} rank={rank}: {complex(outc.re, outc.im)} vs {want}"
+            terms.append((x, y, z)); masks += [qo.getBitMask(x + y), qo.getBitMask(y + z)]
+        arr = (C.c_ulonglong * len(masks))(*masks)
+        outs = (capi.qb_cplx * len(terms))()
+        capi.call("qb_statevec_calcExpecPauliStrBatch_subB", dev.ref, arr, len(terms), outs)
+        for (x, y, z), o in zip(terms, outs):
+            want = qo.statevec_calcExpecPauliStr_subB(st, x, y, z) / qo.POWERS_OF_I[len(y) % 4]
+            assert abs(complex(o.re, o.im) - want) <= TOL
+
+
+def test_scratch_cache_functions():
+    """gpu_getCacheOfSize / gpu_clearCache / gpu_getCacheMemoryInBytes (gpu_config.cpp:639-687): grows monotonically,
+    is reused when large enough, reports its size, and is released by clear"""
+    lib = capi.lib()
+    capi.call("qb_clear_cache")
+    assert lib.qb_cache_bytes() == 0
+    st = C.c_int(0)
+    p1 = lib.qb_get_cache(1000, C.byref(st)); assert p1 and st.value == 0
+    assert lib.qb_cache_bytes() == 1000 * 16
+    p2 = lib.qb_get_cache(10, C.byref(st)); assert p2 == p1 and lib.qb_cache_bytes() == 1000 * 16     # reused, not shrunk
+    p3 = lib.qb_get_cache(5000, C.byref(st)); assert p3 and lib.qb_cache_bytes() == 5000 * 16
+    # the k >= 6 dense path is the cache's user in the reference (gpu_subroutines.cpp:475-498); here it must not disturb it
+    rng = np.random.default_rng(5)
+    s = rand_sv(rng, 10); dev = Dev(s)
+    m = rand_unitary(rng, 64); dm = dev_matrix(m)
+    targs = pick(rng, 10, 6)
+    capi.call("qb_statevec_anyCtrlAnyTargDenseMatr_sub", dev.ref, capi.ints([]), capi.ints([]), 0, capi.ints(targs), 6, dm.data_ptr(), 0)
+    qo.statevec_anyCtrlAnyTargDenseMatr_sub(s, [], [], targs, m, False)
+    check_state(dev, s, "dense6 with a live cache")
+    assert lib.qb_cache_bytes() >= 5000 * 16
+    capi.call("qb_clear_cache")
+    assert lib.qb_cache_bytes() == 0
+
+
+@pytest.mark.parametrize("n", [13, 17])
+def test_interleaved_states_keep_fusing(n):
+    """per-state deferred queues: gates issued alternately on three states (the reference's psi / rho co-evolution
+    pattern, tests/integration/densitymatrix.cpp:68-163) must not flush on every switch"""
+    capi.call("qb_set_tile_engine", 1)
+    rng = np.random.default_rng(2300 + n)
+    sts = [rand_sv(rng, n) for _ in range(3)]
+    devs = [Dev(s) for s in sts]
+    stats0 = (C.c_double * 6)(); capi.call("qb_tile_stats", stats0)
+    launches0 = capi.lib().qb_launch_count()
+    nops = 60
+    for _ in range(nops):
+        for s, d in zip(sts, devs):
+            _random_fusable_op(rng, n, s, d)
+    errs = [rel_l2(d.host(), s.amps) for s, d in zip(sts, devs)]
+    launches = capi.lib().qb_launch_count() - launches0
+    stats1 = (C.c_double * 6)(); capi.call("qb_tile_stats", stats1)
+    assert max(errs) <= TOL * 5, f"interleaved states: rel-L2 {errs}"
+    assert launches < nops, f"switching states flushed the queues: {launches} launches for 3 x {nops} gates"
+    assert stats1[4] - stats0[4] >= 3 * nops * 0.9 and stats1[0] > stats0[0]
