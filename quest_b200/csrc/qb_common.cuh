@@ -10,7 +10,15 @@
 #include <stdio.h>
 #include "../../include/quest_b200.h"
 
+// amplitude type: follows the library's build-time precision (include/quest_b200.h, QuEST's FLOAT_PRECISION)
+#if QB_PRECISION == 1
+typedef float2 cplx;
+typedef float real;
+#else
 typedef double2 cplx;
+typedef double real;
+#endif
+static_assert(sizeof(cplx) == sizeof(qb_cplx), "cplx must be layout-identical to qb_cplx / qcomp");
 typedef long long qindex;
 
 #define QB_MAX_QUBITS 63
@@ -55,16 +63,17 @@ void qb_tile_forget(const void* amps);   // qb_tile.cu: drop the (already flushe
 #define QB_REQUIRE(cond, msg) do { if (!(cond)) return qb_set_error(-1, msg, __FILE__, __LINE__); } while (0)
 
 // ------------------------------------------------------------------------------------------
-// complex arithmetic on double2
+// complex arithmetic on cplx (double2 / float2).  Scalar helpers take `double`: in the fp32 build mixed expressions
+// are evaluated in double and narrowed on assignment, which only ever adds accuracy
 // ------------------------------------------------------------------------------------------
-__host__ __device__ __forceinline__ cplx mk(double re, double im) { cplx c; c.x = re; c.y = im; return c; }
+__host__ __device__ __forceinline__ cplx mk(double re, double im) { cplx c; c.x = (real)re; c.y = (real)im; return c; }
 __host__ __device__ __forceinline__ cplx mk(qb_cplx c) { return mk(c.re, c.im); }
 __host__ __device__ __forceinline__ cplx cadd(cplx a, cplx b) { return mk(a.x + b.x, a.y + b.y); }
 __host__ __device__ __forceinline__ cplx csub(cplx a, cplx b) { return mk(a.x - b.x, a.y - b.y); }
 __host__ __device__ __forceinline__ cplx cmul(cplx a, cplx b) { return mk(a.x * b.x - a.y * b.y, a.x * b.y + a.y * b.x); }
-__host__ __device__ __forceinline__ cplx cscale(double s, cplx a) { return mk(s * a.x, s * a.y); }
+__host__ __device__ __forceinline__ cplx cscale(double s, cplx a) { return mk((real)s * a.x, (real)s * a.y); }
 __host__ __device__ __forceinline__ cplx cconj(cplx a) { return mk(a.x, -a.y); }
-__host__ __device__ __forceinline__ double cnorm(cplx a) { return a.x * a.x + a.y * a.y; }
+__host__ __device__ __forceinline__ double cnorm(cplx a) { return (double)a.x * a.x + (double)a.y * a.y; }
 // acc + a*b
 __host__ __device__ __forceinline__ cplx cfma(cplx a, cplx b, cplx acc) {
     return mk(acc.x + a.x * b.x - a.y * b.y, acc.y + a.x * b.y + a.y * b.x);
@@ -73,12 +82,12 @@ __host__ __device__ __forceinline__ cplx cfma(cplx a, cplx b, cplx acc) {
 // complex power a^b = exp(b * log a), the definition std::pow(complex, complex) uses
 // (reference device version: quest/src/gpu/gpu_types.cuh:248-270)
 __device__ __forceinline__ cplx cpow(cplx a, cplx b) {
-    double r = hypot(a.x, a.y);
+    double r = hypot((double)a.x, (double)a.y);
     if (r == 0.0) {
         // 0^0 = 1, 0^b = 0 (matches std::pow for positive real exponents)
         return (b.x == 0.0 && b.y == 0.0) ? mk(1.0, 0.0) : mk(0.0, 0.0);
     }
-    double lr = log(r), th = atan2(a.y, a.x);
+    double lr = log(r), th = atan2((double)a.y, (double)a.x);
     double ere = b.x * lr - b.y * th;       // Re(b*log a)
     double eim = b.x * th + b.y * lr;       // Im(b*log a)
     double m = exp(ere), s, c;
@@ -167,9 +176,17 @@ static inline unsigned int qb_grid(qindex numItems, int itemsPerThread) {
 // streaming 128-bit accesses. Amplitudes are touched exactly once per pass, so keep them out of L1.
 __device__ __forceinline__ cplx ld_stream(const cplx* p) {
     cplx r;
+#if QB_PRECISION == 1
+    asm volatile("ld.global.L1::no_allocate.v2.f32 {%0, %1}, [%2];" : "=f"(r.x), "=f"(r.y) : "l"(p));
+#else
     asm volatile("ld.global.L1::no_allocate.v2.f64 {%0, %1}, [%2];" : "=d"(r.x), "=d"(r.y) : "l"(p));
+#endif
     return r;
 }
 __device__ __forceinline__ void st_stream(cplx* p, cplx v) {
+#if QB_PRECISION == 1
+    asm volatile("st.global.L1::no_allocate.v2.f32 [%0], {%1, %2};" :: "l"(p), "f"(v.x), "f"(v.y) : "memory");
+#else
     asm volatile("st.global.L1::no_allocate.v2.f64 [%0], {%1, %2};" :: "l"(p), "d"(v.x), "d"(v.y) : "memory");
+#endif
 }

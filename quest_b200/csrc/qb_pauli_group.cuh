@@ -1,0 +1,15 @@
+// qb_pauli_group.cuh -- interface of the coset-blocked Pauli kernels (qb_pauli_group.cu)
+#pragma once
+#include "qb_common.cuh"
+
+#define PG_K 4                       // independent X/Y masks per pass (2^PG_K amplitudes per thread)
+#define PG_AMPS (1 << PG_K)
+#define PG_MAX_OPS 12                // gadgets per pass: PG_K non-diagonal ones plus diagonal ones riding along
+
+// one control-free op: xy != 0: a <- c a + f (-1)^{popc(j & yz)} a_j, j = n ^ xy (f carries i^numY);
+//                      xy == 0: a <- (parity(n & yz) ? f : c) a
+struct PGOp { unsigned long long xy, yz; cplx c, f; };
+
+int pg_rank(const unsigned long long* masks, int k, int* pivots);
+int qb_pauli_group_apply(const qb_state* q, const PGOp* ops, int numOps);
+int qb_pauli_group_expec(const qb_state* q, const unsigned long long* masks, int k, double* devOut);

@@ -84,6 +84,7 @@ int qb_check_qubits(const int* q, int n, int limit) {
 extern "C" {
 
 int qb_abi_version(void) { return 1; }
+int qb_precision(void) { return QB_PRECISION; }
 
 const char* qb_error_string(void) { return t_lastError.c_str(); }
 

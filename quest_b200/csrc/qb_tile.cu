@@ -30,6 +30,7 @@
 #include "qb_common.cuh"
 #include "qb_kernels.cuh"
 #include "qb_tile.cuh"
+#include "qb_pauli_group.cuh"
 #ifdef QB_SELFTEST
 #include "../../include/quest_b200_selftest.h"
 #endif
@@ -206,24 +207,47 @@ QB_HD void reg_dense1(cplx (&v)[RAMPS], cplx m00, cplx m01, cplx m10, cplx m11, 
 }
 
 // K0 < K1; matrix index bit 0 <-> K0, bit 1 <-> K1 (the host re-orders the matrix to make it so); the first matrix row
-// arrives in registers (prefetched while the previous gate ran), the other three are loaded while it is being used
+// arrives in registers (prefetched while the previous gate ran), the other three are loaded while it is being used.
+// QB_D2Q quadruples are updated together, column by column of the matrix: 8 x QB_D2Q independent FMA chains in flight
+// (the FP64 pipe's dependent-issue latency is ~30 cycles at 2 cycles per warp instruction: 8 chains leave it half idle)
+#ifndef QB_D2Q
+#define QB_D2Q 2
+#endif
 template <int K0, int K1, bool CTRL>
 QB_HD void reg_dense2(cplx (&v)[RAMPS], cplx r0, cplx r1, cplx r2, cplx r3, const cplx* __restrict__ mp, unsigned ok) {
+    constexpr int B0 = 1 << K0, B1 = 1 << K1;
+    // the two register bits that are not targets enumerate the four quadruples
+    constexpr int O0 = (K0 != 0 && K1 != 0) ? 0 : ((K0 != 1 && K1 != 1) ? 1 : 2);
+    constexpr int O1 = (K0 != 3 && K1 != 3) ? 3 : ((K0 != 2 && K1 != 2) ? 2 : 1);
     cplx m[16];
     m[0] = r0; m[1] = r1; m[2] = r2; m[3] = r3;
 #pragma unroll
     for (int i = 4; i < 16; i++) m[i] = mp[i];
 #pragma unroll
-    for (int u = 0; u < RAMPS; u++) {
-        if (u & ((1 << K0) | (1 << K1))) continue;
-        const int i1 = u | (1 << K0), i2 = u | (1 << K1), i3 = i1 | (1 << K1);
-        cplx a0 = v[u], a1 = v[i1], a2 = v[i2], a3 = v[i3];
-        const bool c = CTRL ? (bool)((ok >> u) & 1) : true;
-        cplx n0 = cfma(m[3], a3, cfma(m[2], a2, cfma(m[1], a1, cmul(m[0], a0))));
-        cplx n1 = cfma(m[7], a3, cfma(m[6], a2, cfma(m[5], a1, cmul(m[4], a0))));
-        cplx n2 = cfma(m[11], a3, cfma(m[10], a2, cfma(m[9], a1, cmul(m[8], a0))));
-        cplx n3 = cfma(m[15], a3, cfma(m[14], a2, cfma(m[13], a1, cmul(m[12], a0))));
-        v[u] = csel(c, n0, a0); v[i1] = csel(c, n1, a1); v[i2] = csel(c, n2, a2); v[i3] = csel(c, n3, a3);
+    for (int g = 0; g < 4; g += QB_D2Q) {
+        cplx a[QB_D2Q][4], n[QB_D2Q][4];
+#pragma unroll
+        for (int q = 0; q < QB_D2Q; q++) {
+            const int u = (((g + q) & 1) << O0) | (((g + q) >> 1) << O1);
+            a[q][0] = v[u]; a[q][1] = v[u | B0]; a[q][2] = v[u | B1]; a[q][3] = v[u | B0 | B1];
+        }
+#pragma unroll
+        for (int r = 0; r < 4; r++)
+#pragma unroll
+            for (int q = 0; q < QB_D2Q; q++) n[q][r] = cmul(m[4 * r], a[q][0]);
+#pragma unroll
+        for (int c = 1; c < 4; c++)
+#pragma unroll
+            for (int r = 0; r < 4; r++)
+#pragma unroll
+                for (int q = 0; q < QB_D2Q; q++) n[q][r] = cfma(m[4 * r + c], a[q][c], n[q][r]);
+#pragma unroll
+        for (int q = 0; q < QB_D2Q; q++) {
+            const int u = (((g + q) & 1) << O0) | (((g + q) >> 1) << O1);
+            const bool cnd = CTRL ? (bool)((ok >> u) & 1) : true;
+            v[u] = csel(cnd, n[q][0], a[q][0]); v[u | B0] = csel(cnd, n[q][1], a[q][1]);
+            v[u | B1] = csel(cnd, n[q][2], a[q][2]); v[u | B0 | B1] = csel(cnd, n[q][3], a[q][3]);
+        }
     }
 }
 
@@ -309,13 +333,17 @@ QB_HD void reg_round(cplx* __restrict__ t, const RoundHdr& rd, const TileOp* __r
     const TileOp* op = ops + first;
     active >>= first;
 
-    // prefetch of op `q`: dispatch quad + four complex operands
-    int4 d; cplx pa, pb, pc, pd;
-#define PREFETCH(q, D, A, B, C_, D_) do { \
-        D = *reinterpret_cast<const int4*>(q); \
+    // Two-deep software pipeline of the descriptors: while gate o runs, the four complex operands of gate o+1 are
+    // fetched -- which ones depends on its dispatch quad, loaded one gate EARLIER and long since arrived, so no
+    // load sits between two gates -- together with the dispatch quad of gate o+2.
+    int4 d, d1; cplx pa, pb, pc, pd;
+#define LOAD_OPERANDS(q, D, A, B, C_, D_) do { \
         if (D.x >= CODE_STAR) { const StarTab& tb_ = tabs[(q)->tab]; A = QB_LDG(&tb_.in[0][jb & 63]); B = QB_LDG(&tb_.in[1][jb >> 6]); C_ = starF[(q) - ops]; D_ = C_; } \
         else { A = (q)->m[0]; B = (q)->m[1]; C_ = (q)->m[2]; D_ = (q)->m[3]; } } while (0)
-    PREFETCH(op, d, pa, pb, pc, pd);
+    d = *reinterpret_cast<const int4*>(op);
+    d1 = d;
+    if (num > 1) d1 = *reinterpret_cast<const int4*>(op + 1);
+    LOAD_OPERANDS(op, d, pa, pb, pc, pd);
 
     cplx v[RAMPS];
 #pragma unroll
@@ -323,8 +351,10 @@ QB_HD void reg_round(cplx* __restrict__ t, const RoundHdr& rd, const TileOp* __r
     TT_MARK(4);      // address arithmetic + issue of the 16 shared-memory loads
 
     for (int o = 0; o < num; o++, op++, active >>= 1) {
-        int4 dn = d; cplx na = pa, nb = pb, nc_ = pc, nd = pd;
-        if (o + 1 < num) PREFETCH(op + 1, dn, na, nb, nc_, nd);
+        int4 d2 = d1; cplx na = pa, nb = pb, nc_ = pc, nd = pd;
+        if (o + 1 < num) LOAD_OPERANDS(op + 1, d1, na, nb, nc_, nd);
+        if (o + 2 < num) d2 = *reinterpret_cast<const int4*>(op + 2);
+        TT_MARK(10);     // per-gate: issue of the prefetches
         if (active & 1) {
             unsigned ok = 0xFFFFu;
             const unsigned cm = (unsigned)d.z, cv = (unsigned)d.w;
@@ -390,14 +420,15 @@ QB_HD void reg_round(cplx* __restrict__ t, const RoundHdr& rd, const TileOp* __r
                 break;
             }
         }
-        d = dn; pa = na; pb = nb; pc = nc_; pd = nd;
+        TT_MARK(11);     // per-gate: control mask + dispatch + body
+        d = d1; d1 = d2; pa = na; pb = nb; pc = nc_; pd = nd;
     }
-    TT_MARK(5);      // gates (includes waiting for the loads to land)
+    TT_MARK(5);      // loop exit
 #pragma unroll
     for (int u = 0; u < RAMPS; u++) t[jb | OFF(u)] = v[u];
     TT_MARK(6);      // 16 shared-memory stores
   }
-#undef PREFETCH
+#undef LOAD_OPERANDS
 #undef OFF
 }
 
@@ -567,6 +598,8 @@ extern "C" int qb_tile_timing_read(unsigned long long* out12, int reset) {
 // host: planner
 // ------------------------------------------------------------------------------------------
 struct Pass { std::vector<int> opIdx; unsigned long long high = 0; };
+#define PASS_DIRECT (~0ULL)          // Pass::high markers: run the ops one by one through the direct kernels ...
+#define PASS_PGROUP (~1ULL)          // ... or together as one coset-blocked Pauli pass (qb_pauli_group.cu)
 
 static inline unsigned long long nonDiagTargets(const QOp& o) {
     switch (o.kind) {
@@ -948,9 +981,25 @@ static void plan_passes(std::vector<QOp>& ops, bool reorder, std::vector<QOp>& m
     for (size_t i = 0; i < merged.size(); i++) remaining[i] = (int)i;
     while (!remaining.empty()) {
         Pass cur;
-        if (__builtin_popcountll(highNeed(merged[remaining[0]])) > maxHigh) {   // cannot fit any tile (e.g. Pauli string on > 6 high qubits)
-            cur.opIdx.push_back(remaining[0]); cur.high = ~0ULL;                // marker: run direct
-            remaining.erase(remaining.begin());
+        if (__builtin_popcountll(highNeed(merged[remaining[0]])) > maxHigh) {
+            // A Pauli string with X/Y on more than six high qubits fits no tile.  It and the control-free Pauli / parity
+            // gadgets that follow it in program order (Trotter circuits are nothing else) share ONE pass as long as
+            // their X/Y masks stay linearly independent: they only mix amplitudes within cosets of the masks' span
+            unsigned long long masks[PG_K]; int nm = 0; size_t take = 0;
+            for (; take < remaining.size() && take < PG_MAX_OPS; take++) {
+                const QOp& o = merged[remaining[take]];
+                if (o.ctrlMask || (o.kind != OP_PAULI && o.kind != OP_PARITY)) break;
+                if (o.kind == OP_PAULI) {
+                    if (nm == PG_K) break;
+                    masks[nm] = o.maskA;
+                    if (pg_rank(masks, nm + 1, nullptr) != nm + 1) break;
+                    nm++;
+                }
+            }
+            if (take < 2) take = 1;
+            cur.opIdx.assign(remaining.begin(), remaining.begin() + take);
+            cur.high = take >= 2 ? PASS_PGROUP : PASS_DIRECT;
+            remaining.erase(remaining.begin(), remaining.begin() + take);
             passes.push_back(cur);
             continue;
         }
@@ -1015,8 +1064,9 @@ static int flush_one(StateQueue& sq) {
     Emitted E;
     std::vector<int> passKind, passArg;     // -1: direct op index, else index into E.hdrs
     for (auto& p : passes) {
-        bool direct = (p.high == ~0ULL) || (p.opIdx.size() == 1 && merged[p.opIdx[0]].kind != OP_STAR && merged[p.opIdx[0]].kind != OP_HSTAR) || n < TILE_BITS;
-        if (direct) { for (int idx : p.opIdx) { passKind.push_back(-1); passArg.push_back(idx); } }
+        bool direct = (p.high == PASS_DIRECT) || (p.opIdx.size() == 1 && merged[p.opIdx[0]].kind != OP_STAR && merged[p.opIdx[0]].kind != OP_HSTAR) || (n < TILE_BITS && p.high != PASS_PGROUP);
+        if (p.high == PASS_PGROUP && p.opIdx.size() > 1) { passKind.push_back(-2); passArg.push_back((int)(&p - &passes[0])); }
+        else if (direct) { for (int idx : p.opIdx) { passKind.push_back(-1); passArg.push_back(idx); } }
         else {
             passKind.push_back((int)E.hdrs.size()); passArg.push_back(0); emit_pass(&q, merged, p, E, reorder);
             for (int idx : p.opIdx) s_statFmaAmps += fma_per_amp(merged[idx]) * (double)q.numAmpsPerNode;
@@ -1048,6 +1098,20 @@ static int flush_one(StateQueue& sq) {
         attrSet = true;
     }
     for (size_t i = 0; i < passKind.size() && !rc; i++) {
+        if (passKind[i] == -2) {              // coset-blocked Pauli pass
+            const Pass& pp = passes[passArg[i]];
+            PGOp gops[PG_MAX_OPS]; int ng = 0;
+            for (int idx : pp.opIdx) {
+                const QOp& o = merged[idx];
+                PGOp& g = gops[ng++];
+                if (o.kind == OP_PAULI) { g.xy = o.maskA; g.yz = o.maskB; } else { g.xy = 0; g.yz = o.maskA; }
+                g.c = o.m[0]; g.f = o.m[1];
+                s_statFmaAmps += fma_per_amp(o) * (double)q.numAmpsPerNode;
+            }
+            rc = qb_pauli_group_apply(&q, gops, ng);
+            s_statPasses++; s_statTileOps += ng;
+            continue;
+        }
         if (passKind[i] < 0) { rc = run_direct(&q, merged[passArg[i]]); s_statDirectOps++; s_statFmaAmps += fma_per_amp(merged[passArg[i]]) * (double)q.numAmpsPerNode; continue; }
         const int hi = passKind[i];
         s_statPasses++; s_statRounds += E.hdrs[hi].numRounds; s_statTileOps += E.hdrs[hi].numOps;
@@ -1380,7 +1444,7 @@ extern "C" int qb_selftest_planner(int numQubits, int numOps, unsigned seed, int
     plan_passes(queue, reorder != 0, merged, passes);
     int rounds = 0, planned = 0;
     for (const Pass& p : passes) {
-        if (p.high == ~0ULL || n < TILE_BITS) { for (int idx : p.opIdx) { host_apply(got, merged[idx]); planned++; } continue; }
+        if (p.high == PASS_DIRECT || p.high == PASS_PGROUP || n < TILE_BITS) { for (int idx : p.opIdx) { host_apply(got, merged[idx]); planned++; } continue; }
         std::vector<int> order, roundLen, roundKind;
         order_rounds(merged, p, tile_bit_set(n, p), reorder != 0, order, roundLen, roundKind);
         if (order.size() != p.opIdx.size()) return -2;
@@ -1460,8 +1524,8 @@ extern "C" int qb_selftest_tile_emulation(int numQubits, int numOps, unsigned se
     int tilePasses = 0, directOps = 0;
     std::vector<hc> tmp;
     for (const Pass& p : passes) {
-        const bool direct = (p.high == ~0ULL) || (p.opIdx.size() == 1 && merged[p.opIdx[0]].kind != OP_STAR && merged[p.opIdx[0]].kind != OP_HSTAR);
-        if (direct) {                                     // the product runs these through the direct kernels (GPU tests)
+        const bool direct = (p.high == PASS_DIRECT) || (p.high == PASS_PGROUP) || (p.opIdx.size() == 1 && merged[p.opIdx[0]].kind != OP_STAR && merged[p.opIdx[0]].kind != OP_HSTAR);
+        if (direct) {                                     // the product runs these through the direct / coset kernels (GPU tests)
             tmp.resize(state.size());
             for (size_t i = 0; i < state.size(); i++) tmp[i] = tohc(state[i]);
             for (int idx : p.opIdx) { host_apply(tmp, merged[idx]); directOps++; }
@@ -1481,3 +1545,73 @@ extern "C" int qb_selftest_tile_emulation(int numQubits, int numOps, unsigned se
     return 0;
 }
 #endif  // QB_SELFTEST
+
+#ifdef QB_TILE_TIMING
+// ------------------------------------------------------------------------------------------
+// compute-path probe (timing builds only): the round driver on a shared-memory tile, no TMA, no HBM -- what do the
+// gate bodies + dispatch cost per gate with one or two warps per scheduler?  tools/tile_round_probe.py
+// ------------------------------------------------------------------------------------------
+__global__ void __launch_bounds__(TILE_THREADS, 1) k_round_probe(const PassHdr* __restrict__ hdrp, const RoundHdr* __restrict__ grounds,
+        const TileOp* __restrict__ gops, const StarTab* __restrict__ tabs, int reps, double* sink) {
+    extern __shared__ __align__(128) unsigned char smem_raw[];
+    cplx* stageBuf = reinterpret_cast<cplx*>(smem_raw);
+    TileOp* ops = reinterpret_cast<TileOp*>(smem_raw + (size_t)2 * TILE_AMPS * sizeof(cplx));
+    __shared__ RoundHdr rounds[MAX_OPS_PER_PASS];
+    __shared__ cplx starF[MAX_OPS_PER_PASS];
+    const int tid = threadIdx.x, numOps = hdrp->numOps, numRounds = hdrp->numRounds;
+    for (int i = tid; i < numOps * (int)(sizeof(TileOp) / 4); i += blockDim.x) ((int*)ops)[i] = ((const int*)gops)[i];
+    for (int i = tid; i < numRounds * (int)(sizeof(RoundHdr) / 4); i += blockDim.x) ((int*)rounds)[i] = ((const int*)grounds)[i];
+    for (int i = tid; i < 2 * TILE_AMPS; i += blockDim.x) stageBuf[i] = mk(1e-3 * (i & 255), 2e-3 * (i & 127));
+    if (tid < MAX_OPS_PER_PASS) starF[tid] = mk(1, 0);
+    __syncthreads();
+    const int wg = tid / WG_THREADS, wtid = tid % WG_THREADS;
+    cplx* t = stageBuf + (size_t)wg * TILE_AMPS;
+    TT_DECL;
+    for (int rep = 0; rep < reps; rep++)
+        for (int r = 0; r < numRounds; r++) {
+            reg_round(t, rounds[r], ops, 0, ~0ULL, tabs, starF, wtid TT_PASS);
+            wg_sync(wg);
+        }
+    if (wtid == 0) sink[blockIdx.x * 2 + wg] = t[blockIdx.x & 1023].x;
+    TT_FLUSH;
+}
+
+// kind: 1 = dense 1-qubit gates, 2 = dense 2-qubit gates; all on the four highest qubits (one register round)
+extern "C" int qb_tile_round_probe(int kind, int numGates, int numWG, int reps, float* msOut, int* roundsOut) {
+    QB_READY();
+    qb_state q; memset(&q, 0, sizeof q); q.numAmpsPerNode = 1LL << 30; q.logNumAmpsPerNode = 30; q.numQubits = 30;
+    std::vector<QOp> ops;
+    for (int g = 0; g < numGates; g++) {
+        QOp o = blank(kind == 1 ? OP_DENSE1 : OP_DENSE2, &q, 0);
+        if (kind == 1) { o.t0 = 26 + (g & 3); }
+        else { o.numT = 2; o.t0 = (g & 1) ? 28 : 26; o.t1 = o.t0 + 1; }
+        for (int i = 0; i < 16; i++) o.m[i] = mk(0.25 + 0.01 * i, 0.1 - 0.02 * i);
+        ops.push_back(o);
+    }
+    std::vector<QOp> merged; std::vector<Pass> passes;
+    plan_passes(ops, false, merged, passes);
+    if (passes.size() != 1) return qb_set_error(-1, "round probe: expected one pass", __FILE__, __LINE__);
+    Emitted E; emit_pass(&q, merged, passes[0], E, false);
+    if (roundsOut) *roundsOut = E.hdrs[0].numRounds;
+    char* dev; const size_t bh = sizeof(PassHdr), br = E.rounds.size() * sizeof(RoundHdr), bo = E.ops.size() * sizeof(TileOp);
+    QB_CUDA(cudaMalloc(&dev, bh + br + bo + sizeof(StarTab) + 4096));
+    QB_CUDA(cudaMemcpy(dev, E.hdrs.data(), bh, cudaMemcpyHostToDevice));
+    QB_CUDA(cudaMemcpy(dev + bh, E.rounds.data(), br, cudaMemcpyHostToDevice));
+    QB_CUDA(cudaMemcpy(dev + bh + br, E.ops.data(), bo, cudaMemcpyHostToDevice));
+    double* sink = (double*)(dev + bh + br + bo + sizeof(StarTab));
+    const size_t smemBytes = (size_t)2 * TILE_AMPS * sizeof(cplx) + (size_t)MAX_OPS_PER_PASS * sizeof(TileOp);
+    QB_CUDA(cudaFuncSetAttribute(k_round_probe, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smemBytes));
+    cudaEvent_t e0, e1; cudaEventCreate(&e0); cudaEventCreate(&e1);
+    for (int w = 0; w < 2; w++) {
+        cudaEventRecord(e0, g_qb.stream);
+        k_round_probe<<<g_qb.numSMs, WG_THREADS * numWG, smemBytes, g_qb.stream>>>((const PassHdr*)dev, (const RoundHdr*)(dev + bh), (const TileOp*)(dev + bh + br),
+                                                                                   (const StarTab*)(dev + bh + br + bo), reps, sink);
+        cudaEventRecord(e1, g_qb.stream);
+        QB_CUDA(cudaEventSynchronize(e1));
+    }
+    cudaEventElapsedTime(msOut, e0, e1);
+    cudaEventDestroy(e0); cudaEventDestroy(e1);
+    cudaFree(dev);
+    return 0;
+}
+#endif

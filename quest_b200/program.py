@@ -82,11 +82,11 @@ class _Interp:
                 obj = Q.newPauliStrSum(strs, [complex(t[2][0], t[2][1]) for t in v])
                 self.cleanup.append(("destroyPauliStrSum", obj)); return obj
             if k == "amps":
-                arr = np.ascontiguousarray(dec_mat(v), dtype=np.complex128); self.keep.append(arr); return arr.ctypes.data
+                arr = np.ascontiguousarray(dec_mat(v), dtype=qa.np_qcomp); self.keep.append(arr); return arr.ctypes.data
             if k == "out_amps":
-                arr = np.zeros(int(v), dtype=np.complex128); self.outarr = arr; return arr.ctypes.data
+                arr = np.zeros(int(v), dtype=qa.np_qcomp); self.outarr = arr; return arr.ctypes.data
             if k == "out_reals":
-                arr = (C.c_double * int(v))(); self.outarr = arr; return arr
+                arr = (qa.c_qreal * int(v))(); self.outarr = arr; return arr
             raise ValueError(f"unknown argument encoding {k}")
         if isinstance(a, (list, tuple)):
             arr = (C.c_int * max(1, len(a)))(*[int(x) for x in a])

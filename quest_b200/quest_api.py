@@ -9,20 +9,26 @@ and keep process-global singletons: api/environment.cpp:49, core/randomiser.cpp:
 the oracle in a worker subprocess (tests/_worker.py).
 
 Struct layouts mirror quest/include/{qureg.h:49-80, environment.h:33-44, matrices.h:68-230,
-channels.h:74-118, paulis.h:53-80} for FLOAT_PRECISION=2.  qcomp (std::complex<double> /
-double _Complex) is passed and returned BY VALUE as a {double,double} struct, which the SysV x86-64
-ABI classifies identically (two SSE eightbytes).
+channels.h:74-118, paulis.h:53-80}.  qcomp (std::complex<qreal> / qreal _Complex) is passed and returned BY VALUE as a
+{qreal, qreal} struct, which the SysV x86-64 ABI classifies identically.
+
+Precision is a build-time property of a QuEST library (FLOAT_PRECISION, quest/include/precision.h:80-96), so it is an
+import-time property of this binding: QUEST_PRECISION=1 in the environment selects qreal = float (the *_f32 libraries);
+the default is 2 (double).  The test workers set it before importing (tests/_worker.py).
 """
 import ctypes as C
 import os
 import numpy as np
 
-c_qreal = C.c_double
+PRECISION = int(os.environ.get("QUEST_PRECISION", "2"))
+assert PRECISION in (1, 2), "QUEST_PRECISION must be 1 (float) or 2 (double)"
+c_qreal = C.c_float if PRECISION == 1 else C.c_double
+np_qcomp = np.complex64 if PRECISION == 1 else np.complex128
 c_qindex = C.c_longlong
 
 
 class qcomp(C.Structure):
-    _fields_ = [("re", C.c_double), ("im", C.c_double)]
+    _fields_ = [("re", c_qreal), ("im", c_qreal)]
 
     def __complex__(self):
         return complex(self.re, self.im)
@@ -241,7 +247,8 @@ _SIGS = {
 }
 
 REPO_ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
-B200_LIB = os.path.join(REPO_ROOT, "quest_b200", "lib", "libQuEST.so")
+B200_LIB = os.path.join(REPO_ROOT, "quest_b200", "lib", "libQuEST_f32.so" if PRECISION == 1 else "libQuEST.so")
+REF_LIB = os.path.join(REPO_ROOT, "oracle", "_ref_f32" if PRECISION == 1 else "_ref", "libQuEST.so")   # the parity oracle (tests / bench only)
 
 
 def _ints(seq):
@@ -316,8 +323,8 @@ class QuEST:
 
     @staticmethod
     def _view(ptr, n):
-        buf = (C.c_double * (2 * n)).from_address(ptr)
-        return np.frombuffer(buf, dtype=np.complex128)
+        buf = (c_qreal * (2 * n)).from_address(ptr)
+        return np.frombuffer(buf, dtype=np_qcomp)
 
     def newCompMatr(self, m):
         m = np.asarray(m, dtype=np.complex128)
@@ -339,7 +346,7 @@ class QuEST:
         d = np.asarray(d, dtype=np.complex128)
         k = int(round(np.log2(d.size)))
         out = self.lib.createFullStateDiagMatr(k) if custom is None else self.lib.createCustomFullStateDiagMatr(k, *custom)
-        arr = np.ascontiguousarray(d)
+        arr = np.ascontiguousarray(d, dtype=np_qcomp)
         self.lib.setFullStateDiagMatr(out, 0, arr.ctypes.data, d.size)
         return out
 
@@ -381,7 +388,7 @@ class QuEST:
     def getAmps(self, qureg):
         """All amplitudes as a flat complex128 array (density matrices: column-major flat vector)."""
         n = qureg.numAmps
-        out = np.empty(n, dtype=np.complex128)
+        out = np.empty(n, dtype=np_qcomp)
         if qureg.isDensityMatrix:
             # getDensityQuregAmps wants qcomp**; go through the flat statevector view instead
             self.lib.syncQuregFromGpu(qureg) if qureg.isGpuAccelerated else None
@@ -399,7 +406,7 @@ class QuEST:
         return self._view(qureg.cpuAmps, n).copy()
 
     def setAmps(self, qureg, amps):
-        amps = np.ascontiguousarray(amps, dtype=np.complex128)
+        amps = np.ascontiguousarray(amps, dtype=np_qcomp)
         if qureg.isDensityMatrix:
             self.lib.setDensityQuregFlatAmps(qureg, 0, amps.ctypes.data, amps.size)
         else:

@@ -299,19 +299,26 @@ void comm_combineSubArrays(qcomp* recv, vector<qindex> globalRecvInds, vector<qi
 void comm_reduceAmp(qcomp* localAmp) {
     assertDistributedEnv();
     if (s_numRanks == 1) return;
-    QB_CHECK( qb_comm_allreduce_sum(reinterpret_cast<double*>(localAmp), 2) );
+    double v[2] = {(double) std::real(*localAmp), (double) std::imag(*localAmp)};
+    QB_CHECK( qb_comm_allreduce_sum(v, 2) );
+    *localAmp = qcomp((qreal) v[0], (qreal) v[1]);
 }
 
 void comm_reduceReal(qreal* localReal) {
     assertDistributedEnv();
     if (s_numRanks == 1) return;
-    QB_CHECK( qb_comm_allreduce_sum(localReal, 1) );
+    double v = (double) *localReal;
+    QB_CHECK( qb_comm_allreduce_sum(&v, 1) );
+    *localReal = (qreal) v;
 }
 
 void comm_reduceReals(qreal* localReals, qindex numLocalReals) {
     assertDistributedEnv();
     if (s_numRanks == 1) return;
-    QB_CHECK( qb_comm_allreduce_sum(localReals, numLocalReals) );
+    vector<double> v(localReals, localReals + numLocalReals);
+    QB_CHECK( qb_comm_allreduce_sum(v.data(), numLocalReals) );
+    for (qindex i = 0; i < numLocalReals; i++)
+        localReals[i] = (qreal) v[i];
 }
 
 bool comm_isTrueOnAllNodes(bool val) {

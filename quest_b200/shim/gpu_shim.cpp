@@ -556,14 +556,14 @@ INSTANTIATE_FUNC_OPTIMISED_FOR_NUM_TARGS( void, gpu_densmatr_partialTrace_sub, (
 
 qreal gpu_statevec_calcTotalProb_sub(Qureg qureg) {
     auto s = st(qureg);
-    qreal out = 0;
+    double out = 0;      // reductions come back in double in both precisions; narrowed to qreal on return
     QB_CHECK( qb_statevec_calcTotalProb_sub(&s, &out) );
     return out;
 }
 
 qreal gpu_densmatr_calcTotalProb_sub(Qureg qureg) {
     auto s = st(qureg);
-    qreal out = 0;
+    double out = 0;      // reductions come back in double in both precisions; narrowed to qreal on return
     QB_CHECK( qb_densmatr_calcTotalProb_sub(&s, &out) );
     return out;
 }
@@ -572,7 +572,7 @@ template <int NumQubits>
 qreal gpu_statevec_calcProbOfMultiQubitOutcome_sub(Qureg qureg, vector<int> qubits, vector<int> outcomes) {
     assert_numTargsMatchesTemplateParam(qubits.size(), NumQubits);
     auto s = st(qureg);
-    qreal out = 0;
+    double out = 0;      // reductions come back in double in both precisions; narrowed to qreal on return
     QB_CHECK( qb_statevec_calcProbOfMultiQubitOutcome_sub(&s, qubits.data(), outcomes.data(), (int) qubits.size(), &out) );
     return out;
 }
@@ -581,7 +581,7 @@ template <int NumQubits>
 qreal gpu_densmatr_calcProbOfMultiQubitOutcome_sub(Qureg qureg, vector<int> qubits, vector<int> outcomes) {
     assert_numTargsMatchesTemplateParam(qubits.size(), NumQubits);
     auto s = st(qureg);
-    qreal out = 0;
+    double out = 0;      // reductions come back in double in both precisions; narrowed to qreal on return
     QB_CHECK( qb_densmatr_calcProbOfMultiQubitOutcome_sub(&s, qubits.data(), outcomes.data(), (int) qubits.size(), &out) );
     return out;
 }
@@ -590,14 +590,20 @@ template <int NumQubits>
 void gpu_statevec_calcProbsOfAllMultiQubitOutcomes_sub(qreal* outProbs, Qureg qureg, vector<int> qubits) {
     assert_numTargsMatchesTemplateParam(qubits.size(), NumQubits);
     auto s = st(qureg);
-    QB_CHECK( qb_statevec_calcProbsOfAllMultiQubitOutcomes_sub(outProbs, &s, qubits.data(), (int) qubits.size()) );
+    vector<double> probs((size_t) 1 << qubits.size());
+    QB_CHECK( qb_statevec_calcProbsOfAllMultiQubitOutcomes_sub(probs.data(), &s, qubits.data(), (int) qubits.size()) );
+    for (size_t i = 0; i < probs.size(); i++)
+        outProbs[i] = (qreal) probs[i];
 }
 
 template <int NumQubits>
 void gpu_densmatr_calcProbsOfAllMultiQubitOutcomes_sub(qreal* outProbs, Qureg qureg, vector<int> qubits) {
     assert_numTargsMatchesTemplateParam(qubits.size(), NumQubits);
     auto s = st(qureg);
-    QB_CHECK( qb_densmatr_calcProbsOfAllMultiQubitOutcomes_sub(outProbs, &s, qubits.data(), (int) qubits.size()) );
+    vector<double> probs((size_t) 1 << qubits.size());
+    QB_CHECK( qb_densmatr_calcProbsOfAllMultiQubitOutcomes_sub(probs.data(), &s, qubits.data(), (int) qubits.size()) );
+    for (size_t i = 0; i < probs.size(); i++)
+        outProbs[i] = (qreal) probs[i];
 }
 
 INSTANTIATE_FUNC_OPTIMISED_FOR_NUM_TARGS( qreal, gpu_statevec_calcProbOfMultiQubitOutcome_sub, (Qureg, vector<int>, vector<int>) )
@@ -619,7 +625,7 @@ qcomp gpu_statevec_calcInnerProduct_sub(Qureg quregA, Qureg quregB) {
 
 qreal gpu_densmatr_calcHilbertSchmidtDistance_sub(Qureg quregA, Qureg quregB) {
     auto a = st(quregA), b = st(quregB);
-    qreal out = 0;
+    double out = 0;      // reductions come back in double in both precisions; narrowed to qreal on return
     QB_CHECK( qb_densmatr_calcHilbertSchmidtDistance_sub(&a, &b, &out) );
     return out;
 }
@@ -642,7 +648,7 @@ template qcomp gpu_densmatr_calcFidelityWithPureState_sub<false>(Qureg, Qureg);
 
 qreal gpu_statevec_calcExpecAnyTargZ_sub(Qureg qureg, vector<int> targs) {
     auto s = st(qureg);
-    qreal out = 0;
+    double out = 0;      // reductions come back in double in both precisions; narrowed to qreal on return
     QB_CHECK( qb_statevec_calcExpecAnyTargZ_sub(&s, targs.data(), (int) targs.size(), &out) );
     return out;
 }

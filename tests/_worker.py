@@ -8,27 +8,40 @@ import sys
 
 sys.path.insert(0, os.path.dirname(os.path.dirname(os.path.abspath(__file__))))
 
+# `which` ending in "32" selects the single-precision twins (libQuEST_f32.so / oracle/_ref_f32): precision is an
+# import-time property of the binding, like FLOAT_PRECISION is a build-time property of a QuEST library
+if len(sys.argv) > 1 and sys.argv[1].endswith("32"):
+    os.environ["QUEST_PRECISION"] = "1"
+    sys.argv[1] = sys.argv[1][:-2]
+
 from quest_b200 import quest_api as qa          # noqa: E402
 from quest_b200.program import run_program      # noqa: E402
+
+
+CORE_LIB = "libquest_b200_f32.so" if qa.PRECISION == 1 else "libquest_b200.so"
 
 
 def main():
     which, src, dst = sys.argv[1:4]
     progs = pickle.load(open(src, "rb"))
     if which == "ref":
-        Q = qa.QuEST(os.path.join(qa.REPO_ROOT, "oracle", "_ref", "libQuEST.so"))      # the checker: test infrastructure only
+        Q = qa.QuEST(qa.REF_LIB)                 # the checker (oracle/_ref or oracle/_ref_f32): test infrastructure only
         Q.initCustomQuESTEnv(0, 0, 1)            # reference: CPU + OpenMP, the parity oracle
     elif which == "b200dist":
         # one process per GPU (RANK / WORLD_SIZE / LOCAL_RANK from the launcher); every Qureg is sharded
         Q = qa.QuEST(qa.B200_LIB)
         if os.environ.get("QUEST_B200_P2P", "1") == "0":
             import ctypes
-            ctypes.CDLL(os.path.join(os.path.dirname(qa.B200_LIB), "libquest_b200.so"), mode=ctypes.RTLD_GLOBAL).qb_p2p_set_enabled(0)
+            ctypes.CDLL(os.path.join(os.path.dirname(qa.B200_LIB), CORE_LIB), mode=ctypes.RTLD_GLOBAL).qb_p2p_set_enabled(0)
         Q.initCustomQuESTEnv(1, 1, 0)
         dst = dst + "." + os.environ.get("RANK", "0")
     else:
         Q = qa.QuEST(qa.B200_LIB)
         Q.initCustomQuESTEnv(0, 1, 0)            # product: GPU only; fails loudly without a device
+    if qa.PRECISION == 1:
+        # the programs' operators are generated in double and narrowed to float: unitarity / CPTP hold to ~1e-7 per
+        # element, which the reference's own fp32 validation threshold (summed over large matrices) can reject
+        Q.lib.setValidationOff()
     outs = []
     for p in progs:
         if which != "ref":
@@ -42,7 +55,7 @@ def main():
                 assert inf["isGpuAccelerated"] == 1, f"qureg {name} is not GPU-accelerated: refusing CPU path"
         if which == "b200dist":
             import ctypes
-            core = ctypes.CDLL(os.path.join(os.path.dirname(qa.B200_LIB), "libquest_b200.so"), mode=ctypes.RTLD_GLOBAL)
+            core = ctypes.CDLL(os.path.join(os.path.dirname(qa.B200_LIB), CORE_LIB), mode=ctypes.RTLD_GLOBAL)
             out["p2p_available"] = int(core.qb_p2p_is_available())
             out["transport"] = int(core.qb_comm_transport())
         outs.append(out)

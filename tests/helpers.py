@@ -77,7 +77,7 @@ def num_gpus():
         return 0
 
 
-def run_programs_distributed(progs, world, timeout=420, env=None, port=29731):
+def run_programs_distributed(progs, world, timeout=420, env=None, port=29731, which="b200dist"):
     """run the programs on `world` GPUs, one worker process per GPU (the launcher model of the backend:
     RANK / WORLD_SIZE / LOCAL_RANK / MASTER_PORT in the environment, like torchrun).  Returns rank 0's outputs
     with every density-matrix / distributed dump re-assembled from the per-rank shards (rank r holds the
@@ -92,7 +92,7 @@ def run_programs_distributed(progs, world, timeout=420, env=None, port=29731):
             # fewer GPUs than ranks: ranks share devices and the backend switches to its shared-memory / CUDA-IPC transport
             e.update(RANK=str(r), WORLD_SIZE=str(world), LOCAL_RANK=str(r % max(1, num_gpus())), MASTER_ADDR="127.0.0.1", MASTER_PORT=str(port),
                      QUEST_B200_ID_FILE=os.path.join(d, "nccl_id"))
-            procs.append(subprocess.Popen([sys.executable, os.path.join(ROOT, "tests", "_worker.py"), "b200dist", src, dst],
+            procs.append(subprocess.Popen([sys.executable, os.path.join(ROOT, "tests", "_worker.py"), which, src, dst],
                                           stdout=subprocess.PIPE, stderr=subprocess.PIPE, text=True, env=e))
         outs, fails = [], []
         for r, p in enumerate(procs):

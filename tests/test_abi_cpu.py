@@ -137,3 +137,27 @@ def test_tile_kernel_emulation_on_host(n, reorder):
         assert err.value <= 1e-12, f"n={n} seed={seed}: emulated tile passes differ from gate-by-gate application by {err.value:.3e}"
         total_tile_passes += tile_passes.value
     assert total_tile_passes > 0
+
+
+def test_single_precision_twin_library():
+    """FLOAT_PRECISION=1: the fp32 build of the kernel library exports the same ABI and reports its
+    precision; one library per precision, as in the reference"""
+    path = os.path.join(capi.REPO_ROOT, "quest_b200", "lib", "libquest_b200_f32.so")
+    if not os.path.exists(path):
+        pytest.skip("fp32 library not built (make kernels32)")
+    lib32 = C.CDLL(path, mode=C.RTLD_LOCAL)
+    assert lib32.qb_precision() == 1 and capi.lib().qb_precision() == 2
+    missing = [n for n in capi.declared_symbols() if not hasattr(lib32, n)]
+    assert not missing, missing
+
+
+def test_single_precision_reference_pins_to_double_reference():
+    """the fp32 oracle (the reference compiled at FLOAT_PRECISION=1) agrees with the committed fp64 golden outputs to
+    single-precision accuracy -- so it really is the same algorithm at another precision"""
+    from tests import helpers as H
+    if not os.path.exists(os.path.join(capi.REPO_ROOT, "oracle", "_ref_f32", "libQuEST.so")):
+        pytest.skip("oracle/_ref_f32 not built")
+    fx = H.load_golden("configs_small.pkl")
+    outs = H.run_programs("ref32", fx["programs"][:4])
+    for got, want in zip(outs, fx["outputs"][:4]):
+        H.assert_outputs_match(got, want, tol=2e-5, label="fp32 reference vs fp64 golden")

@@ -707,3 +707,72 @@ def test_interleaved_states_keep_fusing(n):
     assert max(errs) <= TOL * 5, f"interleaved states: rel-L2 {errs}"
     assert launches < nops, f"switching states flushed the queues: {launches} launches for 3 x {nops} gates"
     assert stats1[4] - stats0[4] >= 3 * nops * 0.9 and stats1[0] > stats0[0]
+
+
+def _wide_pauli(rng, n, min_sites=8):
+    """a Pauli string with X/Y on many qubits, most of them high: fits no shared-memory tile"""
+    k = int(rng.integers(min_sites, n + 1))
+    t = pick(rng, n, k)
+    chars = rng.choice(list("XYZ"), size=k, p=[0.4, 0.4, 0.2])
+    x = [q for ch, q in zip(chars, t) if ch == "X"]; y = [q for ch, q in zip(chars, t) if ch == "Y"]; z = [q for ch, q in zip(chars, t) if ch == "Z"]
+    return x, y, z
+
+
+@pytest.mark.parametrize("n", [13, 16, 19, 22])
+def test_wide_pauli_gadgets_share_passes(n):
+    """Trotter-like streams: control-free Pauli gadgets on many high qubits, interleaved with Z-only phase gadgets and
+    the occasional repeated (linearly dependent) string.  The engine runs them PG_K at a time through the coset-blocked
+    kernel (quest_b200/csrc/qb_pauli_group.cu); the result must equal gate-by-gate application by the oracle."""
+    capi.call("qb_set_tile_engine", 1)
+    rng = np.random.default_rng(2500 + n)
+    st = rand_sv(rng, n); dev = Dev(st)
+    launches0 = capi.lib().qb_launch_count()
+    nops, last = 45, None
+    for i in range(nops):
+        r = rng.integers(10)
+        if r < 7 or last is None:
+            x, y, z = _wide_pauli(rng, n)
+            if not x and not y:
+                x, z = z[:1], z[1:]
+            last = (x, y, z)
+        elif r < 8:
+            x, y, z = last                                      # the same string again: dependent mask, closes the group
+        else:
+            k = int(rng.integers(1, 6)); t = pick(rng, n, k); f0, f1 = np.exp(1j * rng.uniform(0, 6, 2))
+            capi.call("qb_statevector_anyCtrlAnyTargZOrPhaseGadget_sub", dev.ref, capi.ints([]), capi.ints([]), 0, capi.ints(t), k, capi.cplx(f0), capi.cplx(f1))
+            qo.statevector_anyCtrlAnyTargZOrPhaseGadget_sub(st, [], [], t, f0, f1)
+            continue
+        th = rng.uniform(0, 6); af, pf = complex(np.cos(th)), 1j * np.sin(th)
+        capi.call("qb_statevector_anyCtrlPauliTensorOrGadget_subA", dev.ref, capi.ints([]), capi.ints([]), 0,
+                  capi.ints(x), len(x), capi.ints(y), len(y), capi.ints(z), len(z), capi.cplx(af), capi.cplx(pf))
+        qo.statevector_anyCtrlPauliTensorOrGadget_subA(st, [], [], x, y, z, af, pf)
+    err = rel_l2(dev.host(), st.amps)
+    launches = capi.lib().qb_launch_count() - launches0
+    assert err <= TOL * 5, f"wide gadgets n={n}: rel-L2 {err:.3e}"
+    assert launches <= nops // 2, f"gadgets were not grouped: {launches} launches for {nops} gadgets"
+
+
+@pytest.mark.parametrize("n", [12, 15, 20])
+def test_pauli_expectation_batch_wide_terms(n):
+    """calcExpecPauliStrBatch_subA on a random Hamiltonian-like term list: wide strings (grouped PG_K per pass), Z-only
+    terms, repeated strings and short strings mixed; every term against the oracle's per-term reduction"""
+    rng = np.random.default_rng(2700 + n)
+    st = rand_sv(rng, n); dev = Dev(st)
+    terms, masks = [], []
+    for i in range(37):
+        r = rng.integers(10)
+        if r < 6:
+            x, y, z = _wide_pauli(rng, n, min_sites=min(n, 6))
+        elif r < 7 and terms:
+            x, y, z = terms[-1]
+        elif r < 8:
+            x, y, z = [], [], pick(rng, n, int(rng.integers(1, 5)))
+        else:
+            qs = pick(rng, n, 2); x, y, z = [qs[0]], [qs[1]], []
+        terms.append((x, y, z)); masks += [qo.getBitMask(x + y), qo.getBitMask(y + z)]
+    arr = (C.c_ulonglong * len(masks))(*masks)
+    outs = (capi.qb_cplx * len(terms))()
+    capi.call("qb_statevec_calcExpecPauliStrBatch_subA", dev.ref, arr, len(terms), outs)
+    for k, ((x, y, z), o) in enumerate(zip(terms, outs)):
+        want = qo.statevec_calcExpecPauliStr_subA(st, x, y, z) / qo.POWERS_OF_I[len(y) % 4]
+        assert abs(complex(o.re, o.im) - want) <= TOL, f"term {k} ({x},{y},{z}): {complex(o.re, o.im)} vs {want}"
