@@ -316,6 +316,11 @@ int qb_p2p_anyCtrlOneTargDenseMatr(const qb_state* q, const int* ctrls, const in
  * bit differs from the rank bit trade places. (localiser.cpp:854-869 + gpu_subroutines.cpp:251-280) */
 int qb_p2p_swapHalves(const qb_state* q, int suffixTarg, int pairRank);
 int         qb_p2p_swapHalvesDeferred(const qb_state* q, int suffixTarg, int pairRank); /* same, but may overtake queued gates that do not touch suffixTarg (caller vouches none depends on the rank bit) */
+/* same exchange through the partner's communication buffer on a second stream (copy engines), OVERLAPPED with the deferred
+ * gates of q: they run on the staying half while the leaving half is in flight, then on the arrived half.  Drains q's queue.
+ * Collective over the pair: both ranks must call it (decide from rank-independent state). */
+int         qb_p2p_swapHalvesOverlapped(const qb_state* q, int suffixTarg, int pairRank);
+unsigned long long qb_p2p_overlapped_count(int withQueuedGatesOnly); /* overlapped swaps issued so far (all / those that had gates to overlap) */
 int         qb_queue_info(const qb_state* q, unsigned long long* touchedSuffixMask, unsigned long long* flushEpoch); /* deferred gates of q: count, suffix qubits they involve, flush counter */
 int         qb_p2p_set_swap_mode(int mode);              /* half-shard swap: 0 (default) in-place exchange kernel; 1: kernel push into the partner's buffer + local unpack; 2: copy engines (all within 10%: profiles/) */
 int         qb_p2p_stats(unsigned long long* numExchanges, unsigned long long* linkBytesPerDir); /* peer-memory exchanges issued by this rank so far, and the bytes each sent one way */

@@ -287,7 +287,7 @@ int qb_comm_internal_sync_with(const int* ranks, int numRanks) {
 // host-side rendezvous of a pair when the ranks share a device (qb_p2p.cu: a spinning flag kernel of one process could
 // starve the partner's kernel of the same GPU; the host can simply wait for its own stream and meet the partner)
 bool qb_comm_internal_is_shm() { return s_init && s_shm; }
-int qb_comm_internal_pair_sync_host(int pairRank) {
-    QB_CUDA(cudaStreamSynchronize(g_qb.stream));
+int qb_comm_internal_pair_sync_host(int pairRank, cudaStream_t stream) {
+    QB_CUDA(cudaStreamSynchronize(stream));
     return shm_pair_sync(pairRank);
 }

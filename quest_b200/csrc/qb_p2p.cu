@@ -15,6 +15,7 @@
 // kernel (so neither GPU reads amplitudes the other is still producing, nor runs ahead of remote writes).
 #include "qb_common.cuh"
 #include "qb_kernels.cuh"
+#include "qb_tile.cuh"
 #include <map>
 #include <vector>
 #include <string.h>
@@ -24,7 +25,7 @@ int qb_comm_internal_allgather_host(const void* send, void* recvAll, size_t byte
 int qb_comm_internal_sendrecv_host(const void* send, void* recv, size_t bytes, int pairRank);
 int qb_comm_internal_sync_with(const int* ranks, int numRanks);
 bool qb_comm_internal_is_shm();
-int qb_comm_internal_pair_sync_host(int pairRank);
+int qb_comm_internal_pair_sync_host(int pairRank, cudaStream_t stream);
 
 #define QB_P2P_MAX_RANKS 64
 
@@ -137,15 +138,37 @@ static unsigned long long pair_timeout_ns() {
     return ns;
 }
 
-static int pair_barrier(int pairRank) {
+// The same barrier without the diagnostic printf: <= 32 registers, so that its single warp still finds room on an SM
+// whose register file a persistent k_tile_pass CTA has all but filled (384 x 168 of 65536) -- it runs on the exchange
+// stream WHILE fused passes run on the compute stream (qb_p2p_swapHalvesOverlapped)
+__global__ void __launch_bounds__(32) k_pair_barrier_lean(unsigned long long* peerSlot, volatile unsigned long long* mySlot, unsigned long long epoch, unsigned long long timeoutNs) {
+    if (threadIdx.x) return;
+    __threadfence_system();
+    *(volatile unsigned long long*)peerSlot = epoch;
+    __threadfence_system();
+    unsigned long long t0 = 0;
+    for (unsigned it = 0; *mySlot < epoch; it++) {
+        if ((it & 0xFFF) == 0xFFF) {
+            unsigned long long now;
+            asm volatile("mov.u64 %0, %globaltimer;" : "=l"(now));
+            if (t0 == 0) t0 = now;
+            else if (now - t0 > timeoutNs) __trap();
+        }
+    }
+    __threadfence_system();
+}
+
+static int pair_barrier_on(cudaStream_t stream, int pairRank, bool lean) {
     // ranks sharing one device rendezvous on the host (qb_comm_shm.cu): a spinning kernel would only hold the GPU
     // against the very kernel it is waiting for
-    if (qb_comm_internal_is_shm()) return qb_comm_internal_pair_sync_host(pairRank);
+    if (qb_comm_internal_is_shm()) return qb_comm_internal_pair_sync_host(pairRank, stream);
     unsigned long long epoch = ++s_epoch[pairRank];
-    k_pair_barrier<<<1, 1, 0, g_qb.stream>>>(s_peerFlags[pairRank] + qb_comm_rank(), s_myFlags + pairRank, epoch, pair_timeout_ns());
+    if (lean) k_pair_barrier_lean<<<1, 32, 0, stream>>>(s_peerFlags[pairRank] + qb_comm_rank(), s_myFlags + pairRank, epoch, pair_timeout_ns());
+    else k_pair_barrier<<<1, 1, 0, stream>>>(s_peerFlags[pairRank] + qb_comm_rank(), s_myFlags + pairRank, epoch, pair_timeout_ns());
     QB_LAUNCH_CHECK();
     return 0;
 }
+static int pair_barrier(int pairRank) { return pair_barrier_on(g_qb.stream, pairRank, false); }
 
 // MODE 0: 2x2 dense gate across the pair; MODE 1: swap.  Each item = one amplitude of mine + one of the partner's.
 struct P2POp { BitIns ins; qindex peerXor; int bit; cplx m00, m01, m10, m11; };
@@ -228,7 +251,8 @@ __global__ void __launch_bounds__(QB_BLOCK) k_half_copy(cplx* __restrict__ dst, 
 }
 
 // copies between the strided half "suffix bit s == bitVal" of `shard` and a compact array, with the copy engines
-static int dma_half_copy(cplx* compact, cplx* shard, qindex numAmps, int s, int bitVal, bool toCompact) {
+static int dma_half_copy(cplx* compact, cplx* shard, qindex numAmps, int s, int bitVal, bool toCompact, cudaStream_t stream = nullptr) {
+    if (!stream) stream = g_qb.stream;
     const qindex run = (qindex)1 << s;                     // contiguous amplitudes per row
     const qindex rows = numAmps / (2 * run);
     cplx* strided = shard + (bitVal ? run : 0);
@@ -236,11 +260,11 @@ static int dma_half_copy(cplx* compact, cplx* shard, qindex numAmps, int s, int 
     if (rows <= 16 || pitch > ((size_t)1 << 30)) {
         for (qindex r = 0; r < rows; r++) {
             cplx* a = compact + r * run; cplx* b = strided + 2 * r * run;
-            QB_CUDA(cudaMemcpyAsync(toCompact ? a : b, toCompact ? b : a, width, cudaMemcpyDeviceToDevice, g_qb.stream));
+            QB_CUDA(cudaMemcpyAsync(toCompact ? a : b, toCompact ? b : a, width, cudaMemcpyDeviceToDevice, stream));
         }
     } else {
-        if (toCompact) QB_CUDA(cudaMemcpy2DAsync(compact, width, strided, pitch, width, (size_t)rows, cudaMemcpyDeviceToDevice, g_qb.stream));
-        else           QB_CUDA(cudaMemcpy2DAsync(strided, pitch, compact, width, width, (size_t)rows, cudaMemcpyDeviceToDevice, g_qb.stream));
+        if (toCompact) QB_CUDA(cudaMemcpy2DAsync(compact, width, strided, pitch, width, (size_t)rows, cudaMemcpyDeviceToDevice, stream));
+        else           QB_CUDA(cudaMemcpy2DAsync(strided, pitch, compact, width, width, (size_t)rows, cudaMemcpyDeviceToDevice, stream));
     }
     g_qb.launches += 1;
     return 0;
@@ -288,6 +312,61 @@ int qb_p2p_swapHalvesDeferred(const qb_state* q, int suffixTarg, int pairRank) {
     int queued = qb_queue_info(q, &touched, nullptr);
     if (queued == 0 || ((touched >> suffixTarg) & 1)) QB_FLUSH();      // (a queue of another state is flushed too: cheap and safe)
     return swap_halves(q, suffixTarg, pairRank);
+}
+
+// The swap OVERLAPPED with the deferred gates.  The queued gates commute with the swap when none of them involves
+// `suffixTarg` (nor the rank bit: the caller's promise), and then they act independently on the half of the shard that
+// stays (suffix bit == this rank's bit) and on the half that leaves.  So the leaving half is sent UNPROCESSED, right
+// away, by the copy engines on a second stream into the partner's communication buffer, while the fused passes of
+// the queued gates run on the staying half; when the partner's half has landed it is moved into place and the same
+// passes run on it.  Every amplitude meets every gate exactly once -- on whichever GPU holds it when the gate runs.
+// Unlike swapHalvesDeferred this drains the queue (in two halves) on every rank, and both ranks of the pair must call
+// it (the data path differs from the in-place exchange kernel's): the caller decides from rank-independent state.
+// Reference behaviour replaced: core/localiser.cpp:997-1040 (swap in, apply, swap back -- serial, twice the traffic),
+// comm/comm_routines.cpp:384-407 (device-wide sync before every exchange).
+static unsigned long long s_numOverlapped = 0, s_numOverlappedWithGates = 0;
+extern "C" unsigned long long qb_p2p_overlapped_count(int withQueuedGatesOnly) { return withQueuedGatesOnly ? s_numOverlappedWithGates : s_numOverlapped; }
+static cudaStream_t s_xStream = nullptr;
+static cudaEvent_t s_evReady = nullptr, s_evArrived = nullptr;
+
+int qb_p2p_swapHalvesOverlapped(const qb_state* q, int suffixTarg, int pairRank) {
+    QB_READY_NOFLUSH(); QB_CHECK_STATE(q); QB_CHECK_SUFFIX(&suffixTarg, 1, q);
+    QB_REQUIRE(qb_p2p_is_available(), "p2p path is not available");
+    QB_REQUIRE(q->buffer != nullptr && q->numAmpsPerNode >= 2, "overlapped swap: the state has no communication buffer");
+    unsigned long long touched = 0;
+    int queued = qb_queue_info(q, &touched, nullptr);
+    if ((touched >> suffixTarg) & 1) { QB_FLUSH(); queued = 0; }          // cannot overlap: plain buffered exchange below
+    if (!s_xStream) {
+        QB_CUDA(cudaStreamCreateWithFlags(&s_xStream, cudaStreamNonBlocking));
+        QB_CUDA(cudaEventCreateWithFlags(&s_evReady, cudaEventDisableTiming));
+        QB_CUDA(cudaEventCreateWithFlags(&s_evArrived, cudaEventDisableTiming));
+    }
+    s_numExchanges++; s_linkBytesPerDir += (unsigned long long)q->numAmpsPerNode / 2 * sizeof(cplx);
+    s_numOverlapped++; if (queued) s_numOverlappedWithGates++;
+    const int myBit = qb_comm_rank() > pairRank ? 1 : 0, st = !myBit;     // the half with suffix bit == st leaves
+    void* peerBuf = nullptr;
+    int r = peer_pointer(q->buffer, pairRank, &peerBuf); if (r) return r;
+    const unsigned long long bitMask = 1ULL << suffixTarg;
+
+    // exchange stream: after everything issued so far (the leaving half must be final, the buffers free) ...
+    QB_CUDA(cudaEventRecord(s_evReady, g_qb.stream));
+    QB_CUDA(cudaStreamWaitEvent(s_xStream, s_evReady, 0));
+    r = pair_barrier_on(s_xStream, pairRank, true); if (r) return r;     // ... on BOTH GPUs
+    r = dma_half_copy((cplx*)peerBuf, (cplx*)q->amps, q->numAmpsPerNode, suffixTarg, st, true, s_xStream); if (r) return r;
+    r = pair_barrier_on(s_xStream, pairRank, true); if (r) return r;     // both halves have landed
+    QB_CUDA(cudaEventRecord(s_evArrived, s_xStream));
+
+    // compute stream, meanwhile: the queued gates on the half that stays
+    if (queued) { r = qb_tile_flush_restricted(q, bitMask, myBit ? bitMask : 0, true); if (r) return r; }
+
+    // the arrived half goes where the departed one was, then meets the same gates
+    QB_CUDA(cudaStreamWaitEvent(g_qb.stream, s_evArrived, 0));
+    const qindex half = q->numAmpsPerNode / 2;
+    const BitIns ins = qb_make_ins(&suffixTarg, &st, 1, nullptr, nullptr, 0);
+    k_half_copy<4, false><<<qb_grid(half, 4), QB_BLOCK, 0, g_qb.stream>>>((cplx*)q->amps, (const cplx*)q->buffer, half, ins);
+    QB_LAUNCH_CHECK();
+    if (queued) { r = qb_tile_flush_restricted(q, bitMask, st ? bitMask : 0, false); if (r) return r; }
+    return 0;
 }
 
 static int swap_halves(const qb_state* q, int suffixTarg, int pairRank) {

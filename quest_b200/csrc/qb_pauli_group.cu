@@ -166,13 +166,16 @@ static int pg_upload(const PGDev& h, const PGDev** dev) {
     return 0;
 }
 
-static int pg_build(const qb_state* q, const unsigned long long* xy, int k, PGDev& h) {
+static int pg_build(const qb_state* q, const unsigned long long* xy, int k, PGDev& h, unsigned long long restrictMask = 0, unsigned long long restrictVals = 0) {
     memset(&h, 0, sizeof h);
     int piv[PG_K], zero[PG_K] = {0};
+    int rb[64], rv[64], nr = 0;          // index bits held fixed (restricted pass): extra inserted bits of the representative
+    for (int b = 0; b < 64; b++) if ((restrictMask >> b) & 1) { rb[nr] = b; rv[nr++] = (int)((restrictVals >> b) & 1); }
     QB_REQUIRE(k >= 1 && k <= PG_K && pg_rank(xy, k, piv) == k, "pauli group: masks must be linearly independent");
     for (int i = 0; i < k; i++) QB_REQUIRE(xy[i] < (unsigned long long)q->numAmpsPerNode, "pauli group: X/Y mask reaches prefix qubits");
     h.k = k;
-    h.ins = qb_make_ins(piv, zero, k, nullptr, nullptr, 0);
+    for (int i = 0; i < k; i++) QB_REQUIRE(!(xy[i] & restrictMask), "pauli group: a mask touches a restricted bit");
+    h.ins = qb_make_ins(piv, zero, k, rb, rv, nr);
     for (int g = 0; g < (1 << k); g++) {
         unsigned long long x = 0;
         for (int i = 0; i < k; i++) if ((g >> i) & 1) x ^= xy[i];
@@ -189,12 +192,12 @@ static unsigned pg_sign_bits(const PGDev& h, unsigned long long yz) {
 
 // applies `numOps` control-free Pauli gadgets / tensors (xy != 0) and parity phase gadgets (xy == 0, yz = target mask) in
 // order, in one pass.  The non-zero xy masks must be linearly independent (at most PG_K of them).
-int qb_pauli_group_apply(const qb_state* q, const PGOp* ops, int numOps) {
+int qb_pauli_group_apply(const qb_state* q, const PGOp* ops, int numOps, unsigned long long restrictMask, unsigned long long restrictVals) {
     QB_REQUIRE(numOps >= 1 && numOps <= PG_MAX_OPS, "pauli group: bad op count");
     unsigned long long xy[PG_K]; int k = 0;
     for (int i = 0; i < numOps; i++) if (ops[i].xy) { QB_REQUIRE(k < PG_K, "pauli group: too many X/Y masks"); xy[k++] = ops[i].xy; }
     QB_REQUIRE(k >= 1, "pauli group: needs at least one non-diagonal op");
-    PGDev h; int r = pg_build(q, xy, k, h); if (r) return r;
+    PGDev h; int r = pg_build(q, xy, k, h, restrictMask, restrictVals); if (r) return r;
     h.numOps = numOps;
     int slot = 0;
     for (int i = 0; i < numOps; i++) {
@@ -203,7 +206,7 @@ int qb_pauli_group_apply(const qb_state* q, const PGOp* ops, int numOps) {
         d.yz = (qindex)ops[i].yz; d.sgn = pg_sign_bits(h, ops[i].yz); d.c = ops[i].c; d.f = ops[i].f;
     }
     const PGDev* dev; r = pg_upload(h, &dev); if (r) return r;
-    const qindex groups = q->numAmpsPerNode >> k;
+    const qindex groups = q->numAmpsPerNode >> (k + __builtin_popcountll(restrictMask));
     const unsigned grid = (unsigned)((groups + 127) / 128);
     switch (k) {
     case 1: k_pauli_group<1><<<grid, 128, 0, g_qb.stream>>>((cplx*)q->amps, groups, dev); break;

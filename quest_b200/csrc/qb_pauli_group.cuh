@@ -11,5 +11,5 @@
 struct PGOp { unsigned long long xy, yz; cplx c, f; };
 
 int pg_rank(const unsigned long long* masks, int k, int* pivots);
-int qb_pauli_group_apply(const qb_state* q, const PGOp* ops, int numOps);
+int qb_pauli_group_apply(const qb_state* q, const PGOp* ops, int numOps, unsigned long long restrictMask = 0, unsigned long long restrictVals = 0);
 int qb_pauli_group_expec(const qb_state* q, const unsigned long long* masks, int k, double* devOut);

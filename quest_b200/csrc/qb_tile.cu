@@ -88,6 +88,11 @@ static unsigned long long s_flushEpoch = 0;       // bumped whenever a non-empty
 // cumulative execution statistics (qb_tile_stats): what the planner made of the gates it was given
 static unsigned long long s_statPasses = 0, s_statRounds = 0, s_statTileOps = 0, s_statDirectOps = 0, s_statQueuedGates = 0;
 static double s_statFmaAmps = 0;                   // FP64 fused multiply-adds issued per pass, summed: ops x amplitudes x FMA per amplitude
+// Restricted flush (qb_tile_flush_restricted): the queue is applied only to the amplitudes whose index bits `mask`
+// hold `vals` -- as if every queued gate carried those extra controls, but without disturbing gate absorption or the
+// phase-star merge (the restriction is a property of the passes: whole tiles are pruned).  Used to overlap a
+// half-shard exchange with the gates that commute with it (qb_p2p.cu).
+static unsigned long long s_restrictMask = 0, s_restrictVals = 0;
 
 // device-side op, in tile coordinates
 struct TileOp {
@@ -714,7 +719,7 @@ struct Emitted {
 // tile bit set of a pass: the low bits, the required high bits, then filler (lowest unused bits) up to TILE_BITS
 static unsigned long long tile_bit_set(int n, const Pass& pass) {
     unsigned long long S = ((1ULL << TILE_LOW) - 1) | pass.high;
-    for (int b = TILE_LOW; b < n && __builtin_popcountll(S) < TILE_BITS; b++) S |= 1ULL << b;
+    for (int b = TILE_LOW; b < n && __builtin_popcountll(S) < TILE_BITS; b++) if (!((s_restrictMask >> b) & 1)) S |= 1ULL << b;
     return S;
 }
 
@@ -764,6 +769,7 @@ static void emit_pass(const qb_state* q, const std::vector<QOp>& ops, const Pass
         else { common &= m; common &= ~((o.ctrlVals ^ commonVals) & common); commonVals &= common; }
     }
 
+    common |= s_restrictMask & ~S; commonVals = (commonVals & ~s_restrictMask) | (s_restrictVals & s_restrictMask & ~S);
     PassHdr h; memset(&h, 0, sizeof h);
     int contiguous = 0; while (contiguous < T && sbits[contiguous] == contiguous) contiguous++;
     h.chunkAmps = 1 << contiguous;
@@ -1026,6 +1032,7 @@ static void plan_passes(std::vector<QOp>& ops, bool reorder, std::vector<QOp>& m
 // FP64 fused multiply-adds per touched amplitude of each op kind (complex arithmetic written out: cmul = 4, cfma = 4)
 static double fma_per_amp(const QOp& o) {
     double f;
+    const double share = 1.0 / (double)(1ULL << __builtin_popcountll(s_restrictMask));
     switch (o.kind) {
     case OP_DENSE1: f = 8; break;
     case OP_DENSE2: f = 16; break;
@@ -1034,7 +1041,7 @@ static double fma_per_amp(const QOp& o) {
     case OP_HSTAR: f = 7; break;
     default: f = 4; break;                    // diagonal / parity / star: one complex multiply
     }
-    return f / (double)(1ULL << __builtin_popcountll(o.ctrlMask));
+    return share * f / (double)(1ULL << __builtin_popcountll(o.ctrlMask));
 }
 
 static int flush_one(StateQueue& sq);
@@ -1108,7 +1115,7 @@ static int flush_one(StateQueue& sq) {
                 g.c = o.m[0]; g.f = o.m[1];
                 s_statFmaAmps += fma_per_amp(o) * (double)q.numAmpsPerNode;
             }
-            rc = qb_pauli_group_apply(&q, gops, ng);
+            rc = qb_pauli_group_apply(&q, gops, ng, s_restrictMask, s_restrictVals);
             s_statPasses++; s_statTileOps += ng;
             continue;
         }
@@ -1159,6 +1166,21 @@ extern "C" int qb_tile_stats(double out[6]) {
     out[0] = (double)s_statPasses; out[1] = (double)s_statRounds; out[2] = (double)s_statTileOps; out[3] = (double)s_statDirectOps;
     out[4] = (double)s_statQueuedGates; out[5] = s_statFmaAmps;
     return 0;
+}
+
+// Runs the queue of `q` on the half (quarter ...) of the shard whose index bits `mask` hold `vals`.  keepQueue: the gates
+// stay queued (the caller will run them on the remaining amplitudes later).  No queued gate may involve a bit of `mask`.
+int qb_tile_flush_restricted(const qb_state* q, unsigned long long mask, unsigned long long vals, bool keepQueue) {
+    StateQueue* sq = find_queue(q);
+    if (!sq || sq->ops.empty() || s_inFlush) return 0;
+    for (const QOp& o : sq->ops)
+        if ((nonDiagTargets(o) | diagQubits(o)) & mask) return qb_set_error(-1, "restricted flush: a queued gate involves a restricted bit", __FILE__, __LINE__);
+    StateQueue work = *sq;
+    if (!keepQueue) sq->ops.clear();
+    s_restrictMask = mask; s_restrictVals = vals & mask;
+    int r = flush_one(work);
+    s_restrictMask = s_restrictVals = 0;
+    return r;
 }
 
 // called by qb_free: whatever is still queued for memory about to be released must run first (QB_READY in qb_free
@@ -1277,7 +1299,8 @@ int qb_tile_try_swap(const qb_state* q, const int* ctrls, const int* cs, int nc,
 // ------------------------------------------------------------------------------------------
 static int run_direct(const qb_state* q, const QOp& o) {
     int ctrls[64], cs[64], nc = 0;
-    for (int b = 0; b < 64; b++) if ((o.ctrlMask >> b) & 1) { ctrls[nc] = b; cs[nc++] = (int)((o.ctrlVals >> b) & 1); }
+    const unsigned long long cmask = o.ctrlMask | s_restrictMask, cvals = (o.ctrlVals & ~s_restrictMask) | s_restrictVals;
+    for (int b = 0; b < 64; b++) if ((cmask >> b) & 1) { ctrls[nc] = b; cs[nc++] = (int)((cvals >> b) & 1); }
     qb_cplx m[16];
     for (int i = 0; i < 16; i++) { m[i].re = o.m[i].x; m[i].im = o.m[i].y; }
     switch (o.kind) {
@@ -1297,15 +1320,15 @@ static int run_direct(const qb_state* q, const QOp& o) {
     case OP_HSTAR: {
         const double s = 0.70710678118654752440;
         qb_cplx h[4] = {{s, 0}, {s, 0}, {s, 0}, {-s, 0}};
-        int r = qb_statevec_anyCtrlOneTargDenseMatr_subA(q, ctrls, cs, 0, o.t0, h);
+        int r = qb_statevec_anyCtrlOneTargDenseMatr_subA(q, ctrls, cs, nc, o.t0, h);
         if (r) return r;
     }   // fall through: then the star's controlled phases
     case OP_STAR: {
         // a star that did not end up in a tile pass: apply its controlled phases one by one
         for (auto& ce : o.star) {
-            int c = ce.first; int one = 1;
-            qb_cplx e[2] = {{1, 0}, {cos(ce.second), sin(ce.second)}};
-            int r = qb_statevec_anyCtrlOneTargDiagMatr_sub(q, &c, &one, 1, o.t0, e);
+            ctrls[nc] = ce.first; cs[nc] = 1;
+            qb_cplx e[2] = {{1, 0}, {(qb_real)cos(ce.second), (qb_real)sin(ce.second)}};
+            int r = qb_statevec_anyCtrlOneTargDiagMatr_sub(q, ctrls, cs, nc + 1, o.t0, e);
             if (r) return r;
         }
         return 0;

@@ -14,3 +14,6 @@ int qb_tile_try_swap(const qb_state* q, const int* ctrls, const int* cs, int nc,
 
 // direct Pauli kernel from raw masks (pairFac already multiplied by i^numY); qb_gates.cu
 int qb_pauli_raw(const qb_state* q, const int* ctrls, const int* cs, int nc, unsigned long long maskXY, unsigned long long maskYZ, qb_cplx ampFac, qb_cplx pairFac);
+
+// applies the deferred gates of q to the amplitudes whose index bits `mask` hold `vals` only (see qb_tile.cu)
+int qb_tile_flush_restricted(const qb_state* q, unsigned long long mask, unsigned long long vals, bool keepQueue);

@@ -219,6 +219,13 @@ static bool relabelEnabled() {
     return on == 1;
 }
 
+// QUEST_B200_OVERLAP=0 keeps every swap-in on the in-place exchange kernel (serial with the compute stream)
+static bool overlapEnabled() {
+    static int on = -1;
+    if (on < 0) { const char* e = std::getenv("QUEST_B200_OVERLAP"); on = (e && e[0] == '0') ? 0 : 1; }
+    return on == 1;
+}
+
 static bool mapEligible(Qureg q) {
     return relabelEnabled() && q.isGpuAccelerated && !q.isDensityMatrix && q.gpuAmps != nullptr && q.numQubits <= 62;
 }
@@ -359,7 +366,15 @@ static bool pullTargetsIntoShard(Qureg qureg, QubitMap& m, vector<int>& targs, c
         }
         if (victim < 0) return false;
 
-        if (mayOvertake)
+        // gates are waiting and none of them involves the victim: exchange through the buffers on a second stream while
+        // they run on the half that stays (every rank takes this branch together: the test uses rank-independent state)
+        bool overlap = mayOvertake && overlapEnabled() && queued && !((touched >> victim) & 1)
+                    && qureg.gpuCommBuffer != nullptr && victim >= 10;
+        if (overlap) {
+            QB_CHECK( qb_p2p_swapHalvesOverlapped(&st, victim, rankWithFlipped(qureg, {targs[i]})) );
+            g_queuedBits.erase(qureg.gpuAmps);          // every rank has drained its queue inside the call
+        }
+        else if (mayOvertake)
             QB_CHECK( qb_p2p_swapHalvesDeferred(&st, victim, rankWithFlipped(qureg, {targs[i]})) );
         else {
             swapPrefixWithSuffix(qureg, {}, {}, victim, targs[i]);      // flushes the queue on every rank

@@ -58,6 +58,8 @@ def main():
             core = ctypes.CDLL(os.path.join(os.path.dirname(qa.B200_LIB), CORE_LIB), mode=ctypes.RTLD_GLOBAL)
             out["p2p_available"] = int(core.qb_p2p_is_available())
             out["transport"] = int(core.qb_comm_transport())
+            core.qb_p2p_overlapped_count.restype = ctypes.c_ulonglong
+            out["overlapped_swaps"] = int(core.qb_p2p_overlapped_count(1))
         outs.append(out)
     Q.finalizeQuESTEnv()
     pickle.dump(outs, open(dst, "wb"))

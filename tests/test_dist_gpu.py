@@ -55,9 +55,21 @@ def test_lazy_qubit_relabelling_sharded(world, p2p):
     logp = world.bit_length() - 1
     # the last program is long enough to overflow the backend's 2048-gate queue while gates with rank-bit controls have
     # been dropped on some ranks only (the ranks' queues then differ in length)
-    _check([P.relabel_program(logp + 3, 6301), P.relabel_program(logp + 7, 6302), P.relabel_program(logp + 13, 6303, num_ops=120),
-            P.relabel_program(logp + 13, 6304, num_ops=2600, reads=False)],
-           world, env={"QUEST_B200_P2P": p2p})
+    got = _check([P.relabel_program(logp + 3, 6301), P.relabel_program(logp + 7, 6302), P.relabel_program(logp + 13, 6303, num_ops=120),
+                  P.relabel_program(logp + 13, 6304, num_ops=2600, reads=False)],
+                 world, env={"QUEST_B200_P2P": p2p})
+    if p2p == "1":
+        # the exchange overlapped with the deferred gates (qb_p2p_swapHalvesOverlapped) must have been part of what ran
+        assert got[-1]["overlapped_swaps"] > 0, "no swap-in overlapped queued gates"
+
+
+@pytest.mark.skipif(not WORLDS, reason="needs a GPU")
+@pytest.mark.parametrize("world", WORLDS)
+def test_swap_in_without_overlap_sharded(world):
+    """QUEST_B200_OVERLAP=0: every swap-in through the in-place exchange kernel, the queue overtaken but not split"""
+    logp = world.bit_length() - 1
+    got = _check([P.relabel_program(logp + 13, 6303, num_ops=120), P.cfg2_program(logp + 13, 6403, 40)], world, env={"QUEST_B200_OVERLAP": "0"})
+    assert got[-1]["overlapped_swaps"] == 0
 
 
 @pytest.mark.skipif(not WORLDS, reason="needs a GPU")

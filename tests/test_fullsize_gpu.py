@@ -81,8 +81,9 @@ FULLSIZE = {"fullsize_cfg2_30q.pkl": cfg2_fullsize_program, "fullsize_cfg4_14q_d
 def _reference_outputs(fname, prog):
     if not LIVE:
         fx = H.load_golden(fname)
-        assert fx["programs"][0]["ops"][:50] == prog["ops"][:50] and len(fx["programs"][0]["ops"]) == len(prog["ops"]), \
-            f"{fname} was generated from a different program: re-run tests/golden/make_fullsize.py"
+        def sig(p):      # the API calls and their integer arguments (matrices are regenerated from the same seeds)
+            return [[a for a in op if isinstance(a, (str, int, float))] for op in p["ops"]]
+        assert sig(fx["programs"][0]) == sig(prog), f"{fname} was generated from a different program: re-run tests/golden/make_fullsize.py"
         return None, fx["outputs"][0]
     if not os.path.exists(H.REF_LIB):
         pytest.skip("oracle/_ref/libQuEST.so not present")
