@@ -228,8 +228,9 @@ static void my_share(qindex total, int pairRank, qindex* first, qindex* count) {
 //   own buffer into place.  mode 2 (copy-engine push): the same two steps issued as cudaMemcpy(2D)Async.
 // mode 0: the in-place exchange kernel (each GPU reads and writes half of the pairs remotely; no buffer needed).
 static int s_swapMode = -1;
+static bool s_swapModeIsDefault = true;
 static int swap_mode() {
-    if (s_swapMode < 0) { const char* e = getenv("QUEST_B200_SWAP_MODE"); s_swapMode = e ? atoi(e) : 0; if (s_swapMode < 0 || s_swapMode > 2) s_swapMode = 0; }
+    if (s_swapMode < 0) { const char* e = getenv("QUEST_B200_SWAP_MODE"); s_swapModeIsDefault = (e == nullptr); s_swapMode = e ? atoi(e) : 0; if (s_swapMode < 0 || s_swapMode > 2) s_swapMode = 0; }
     return s_swapMode;
 }
 
@@ -348,16 +349,28 @@ int qb_p2p_swapHalvesOverlapped(const qb_state* q, int suffixTarg, int pairRank)
     int r = peer_pointer(q->buffer, pairRank, &peerBuf); if (r) return r;
     const unsigned long long bitMask = 1ULL << suffixTarg;
 
+    // optional timeline of one call (QUEST_B200_OVERLAP_TRACE=1): synchronises, so for diagnosis only
+    static int trace = -1;
+    if (trace < 0) { const char* e = getenv("QUEST_B200_OVERLAP_TRACE"); trace = (e && e[0] == '1') ? 1 : 0; }
+    cudaEvent_t tv[7];
+    if (trace) for (int i = 0; i < 7; i++) cudaEventCreate(&tv[i]);
+#define TRACE(i, stream) do { if (trace) cudaEventRecord(tv[i], stream); } while (0)
+
     // exchange stream: after everything issued so far (the leaving half must be final, the buffers free) ...
+    TRACE(0, g_qb.stream);
     QB_CUDA(cudaEventRecord(s_evReady, g_qb.stream));
     QB_CUDA(cudaStreamWaitEvent(s_xStream, s_evReady, 0));
     r = pair_barrier_on(s_xStream, pairRank, true); if (r) return r;     // ... on BOTH GPUs
+    TRACE(1, s_xStream);
     r = dma_half_copy((cplx*)peerBuf, (cplx*)q->amps, q->numAmpsPerNode, suffixTarg, st, true, s_xStream); if (r) return r;
+    TRACE(2, s_xStream);
     r = pair_barrier_on(s_xStream, pairRank, true); if (r) return r;     // both halves have landed
+    TRACE(3, s_xStream);
     QB_CUDA(cudaEventRecord(s_evArrived, s_xStream));
 
     // compute stream, meanwhile: the queued gates on the half that stays
     if (queued) { r = qb_tile_flush_restricted(q, bitMask, myBit ? bitMask : 0, true); if (r) return r; }
+    TRACE(4, g_qb.stream);
 
     // the arrived half goes where the departed one was, then meets the same gates
     QB_CUDA(cudaStreamWaitEvent(g_qb.stream, s_evArrived, 0));
@@ -365,7 +378,17 @@ int qb_p2p_swapHalvesOverlapped(const qb_state* q, int suffixTarg, int pairRank)
     const BitIns ins = qb_make_ins(&suffixTarg, &st, 1, nullptr, nullptr, 0);
     k_half_copy<4, false><<<qb_grid(half, 4), QB_BLOCK, 0, g_qb.stream>>>((cplx*)q->amps, (const cplx*)q->buffer, half, ins);
     QB_LAUNCH_CHECK();
+    TRACE(5, g_qb.stream);
     if (queued) { r = qb_tile_flush_restricted(q, bitMask, st ? bitMask : 0, false); if (r) return r; }
+    TRACE(6, g_qb.stream);
+#undef TRACE
+    if (trace) {
+        cudaDeviceSynchronize();
+        float t[7]; for (int i = 1; i < 7; i++) cudaEventElapsedTime(&t[i], tv[0], tv[i]);
+        fprintf(stderr, "[overlap rank %d] victim %d queued %d | xs: barrier1 %.2f copy-done %.2f barrier2 %.2f | compute: stay-half done %.2f unpack done %.2f arrived-half done %.2f ms\n",
+                qb_comm_rank(), suffixTarg, queued, t[1], t[2], t[3], t[4], t[5], t[6]);
+        for (int i = 0; i < 7; i++) cudaEventDestroy(tv[i]);
+    }
     return 0;
 }
 
@@ -377,7 +400,11 @@ static int swap_halves(const qb_state* q, int suffixTarg, int pairRank) {
     // where myBit is this rank's value of the prefix qubit: myBit = 1 iff rank > pairRank (they differ in that bit only)
     int myBit = qb_comm_rank() > pairRank ? 1 : 0;
     int st = !myBit;
-    const int mode = (q->buffer != nullptr && q->numAmpsPerNode >= 2) ? swap_mode() : 0;
+    // default (QUEST_B200_SWAP_MODE unset): the copy engines push through the buffers when the rows are long (>= 64 KiB):
+    // 8 GiB in 11.05 ms = 777 GB/s per direction + 2.5 ms local unpack, against 14.7 ms for the in-place kernel
+    // (profiles/r2_overlap_trace_2gpu.txt); short rows and buffer-less states use the in-place exchange kernel
+    int mode = (q->buffer != nullptr && q->numAmpsPerNode >= 2) ? swap_mode() : 0;
+    if (s_swapModeIsDefault && q->buffer != nullptr && suffixTarg >= 12) mode = 2;
     int r;
     if (mode == 0) {
         r = peer_pointer(q->amps, pairRank, &peer); if (r) return r;
@@ -410,6 +437,6 @@ extern "C" int qb_p2p_stats(unsigned long long* numExchanges, unsigned long long
     return 0;
 }
 
-extern "C" int qb_p2p_set_swap_mode(int mode) { s_swapMode = (mode < 0 || mode > 2) ? 0 : mode; return 0; }
+extern "C" int qb_p2p_set_swap_mode(int mode) { s_swapMode = (mode < 0 || mode > 2) ? 0 : mode; s_swapModeIsDefault = false; return 0; }
 
 } // extern "C"

@@ -183,6 +183,7 @@ static unsigned long long g_mapSeq = 0;
 // (collectiveFlush: restoring the canonical order, syncQuESTEnv, a flushing swap-in).
 static std::unordered_map<const void*, bool> g_rankBitsPinned;
 static std::unordered_map<const void*, unsigned long long> g_queuedBits;
+static std::unordered_map<const void*, int> g_queuedGates;       // gates handed to the backend since the last collective flush
 
 static void noteGateQubits(Qureg q, const vector<int>& physQubits) {
     if (!q.isDistributed || !q.isGpuAccelerated || q.isDensityMatrix) return;
@@ -190,6 +191,7 @@ static void noteGateQubits(Qureg q, const vector<int>& physQubits) {
         if (b >= q.logNumAmpsPerNode) g_rankBitsPinned[q.gpuAmps] = true;
         else g_queuedBits[q.gpuAmps] |= 1ULL << b;
     }
+    g_queuedGates[q.gpuAmps]++;          // (called once or twice per gate: an upper bound is all that is needed)
 }
 
 static bool rankBitsPinned(Qureg q) {
@@ -208,6 +210,7 @@ static void collectiveFlush(Qureg q) {
     if (g_queuedBits.empty() && g_rankBitsPinned.empty()) return;
     QB_CHECK( qb_flush() );
     g_queuedBits.erase(q.gpuAmps);
+    g_queuedGates.erase(q.gpuAmps);
     g_rankBitsPinned.erase(q.gpuAmps);
 }
 
@@ -224,6 +227,12 @@ static bool overlapEnabled() {
     static int on = -1;
     if (on < 0) { const char* e = std::getenv("QUEST_B200_OVERLAP"); on = (e && e[0] == '0') ? 0 : 1; }
     return on == 1;
+}
+
+static int overlapMinGates() {
+    static int n = -1;
+    if (n < 0) { const char* e = std::getenv("QUEST_B200_OVERLAP_MIN_GATES"); n = e ? std::atoi(e) : 48; if (n < 1) n = 1; }
+    return n;
 }
 
 static bool mapEligible(Qureg q) {
@@ -305,6 +314,7 @@ void qbmap_forget(const void* gpuAmps) {
     if (!g_qubitMaps.empty()) g_qubitMaps.erase(gpuAmps);
     g_rankBitsPinned.erase(gpuAmps);
     g_queuedBits.erase(gpuAmps);
+    g_queuedGates.erase(gpuAmps);
 }
 
 void qbmap_canonicaliseHolding(const void* gpuPtr) {
@@ -329,6 +339,7 @@ void qbmap_canonicaliseAll() {
     if (!g_queuedBits.empty() || !g_rankBitsPinned.empty()) {
         QB_CHECK( qb_flush() );
         g_queuedBits.clear();
+        g_queuedGates.clear();
         g_rankBitsPinned.clear();
     }
 }
@@ -368,11 +379,17 @@ static bool pullTargetsIntoShard(Qureg qureg, QubitMap& m, vector<int>& targs, c
 
         // gates are waiting and none of them involves the victim: exchange through the buffers on a second stream while
         // they run on the half that stays (every rank takes this branch together: the test uses rank-independent state)
+        // Overlapping drains the queue (in two halves), which shortens the planner's fusion window, so it pays only when
+        // enough work is waiting to hide the ~11 ms transfer behind (measured: profiles/r2_overlap_trace_2gpu.txt);
+        // smaller queues are overtaken instead and keep growing
+        auto qg = g_queuedGates.find(qureg.gpuAmps);
         bool overlap = mayOvertake && overlapEnabled() && queued && !((touched >> victim) & 1)
-                    && qureg.gpuCommBuffer != nullptr && victim >= 10;
+                    && qureg.gpuCommBuffer != nullptr && victim >= 10
+                    && qg != g_queuedGates.end() && qg->second >= overlapMinGates();
         if (overlap) {
             QB_CHECK( qb_p2p_swapHalvesOverlapped(&st, victim, rankWithFlipped(qureg, {targs[i]})) );
             g_queuedBits.erase(qureg.gpuAmps);          // every rank has drained its queue inside the call
+            g_queuedGates.erase(qureg.gpuAmps);
         }
         else if (mayOvertake)
             QB_CHECK( qb_p2p_swapHalvesDeferred(&st, victim, rankWithFlipped(qureg, {targs[i]})) );
@@ -380,6 +397,7 @@ static bool pullTargetsIntoShard(Qureg qureg, QubitMap& m, vector<int>& targs, c
             swapPrefixWithSuffix(qureg, {}, {}, victim, targs[i]);      // flushes the queue on every rank
             g_rankBitsPinned.erase(qureg.gpuAmps);
             g_queuedBits.erase(qureg.gpuAmps);
+            g_queuedGates.erase(qureg.gpuAmps);
         }
         int lt = m.logi[targs[i]], lv = m.logi[victim];
         m.logi[targs[i]] = lv; m.logi[victim] = lt;

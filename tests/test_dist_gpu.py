@@ -57,7 +57,7 @@ def test_lazy_qubit_relabelling_sharded(world, p2p):
     # been dropped on some ranks only (the ranks' queues then differ in length)
     got = _check([P.relabel_program(logp + 3, 6301), P.relabel_program(logp + 7, 6302), P.relabel_program(logp + 13, 6303, num_ops=120),
                   P.relabel_program(logp + 13, 6304, num_ops=2600, reads=False)],
-                 world, env={"QUEST_B200_P2P": p2p})
+                 world, env={"QUEST_B200_P2P": p2p, "QUEST_B200_OVERLAP_MIN_GATES": "3"})      # overlap even short queues
     if p2p == "1":
         # the exchange overlapped with the deferred gates (qb_p2p_swapHalvesOverlapped) must have been part of what ran
         assert got[-1]["overlapped_swaps"] > 0, "no swap-in overlapped queued gates"
