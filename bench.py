@@ -373,20 +373,26 @@ def secondary_configs(P, n_local, full):
         it.quregs = quregs
         results = []
 
+        # operands (heap matrices, Kraus maps, Pauli sums) are created ONCE, outside the timed region: a user builds a
+        # channel or a Hamiltonian once and applies it many times; creating and freeing device objects per call would time
+        # cudaMalloc/cudaFree (which synchronise the device), not the operators
+        calls = []
+        for op in prog["ops"]:
+            it.keep, it.outarr = [], None
+            cargs = [it.conv(a) for a in op[1:]]
+            calls.append((getattr(Q.lib, op[0]), cargs, it.keep))
+        made = list(it.cleanup); it.cleanup.clear()
+
         def body():
             for name, spec in prog["quregs"].items():
                 Q.initPlusState(quregs[name])
             results.clear()
-            for op in prog["ops"]:
-                it.keep, it.outarr = [], None
-                cargs = [it.conv(a) for a in op[1:]]
-                r = getattr(Q.lib, op[0])(*cargs)
-                results.append(r)
-                for fn, obj in it.cleanup:
-                    getattr(Q.lib, fn)(obj)
-                it.cleanup.clear()
+            for fn, cargs, _keep in calls:
+                results.append(fn(*cargs))
             Q.syncQuESTEnv()
         ms = P.timed(body, reps, 1)
+        for fn, obj in made:
+            getattr(Q.lib, fn)(obj)
         for qq in quregs.values():
             Q.destroyQureg(qq)
         return ms, list(results)

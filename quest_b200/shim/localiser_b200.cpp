@@ -231,7 +231,7 @@ static bool overlapEnabled() {
 
 static int overlapMinGates() {
     static int n = -1;
-    if (n < 0) { const char* e = std::getenv("QUEST_B200_OVERLAP_MIN_GATES"); n = e ? std::atoi(e) : 48; if (n < 1) n = 1; }
+    if (n < 0) { const char* e = std::getenv("QUEST_B200_OVERLAP_MIN_GATES"); n = e ? std::atoi(e) : 16; if (n < 1) n = 1; }
     return n;
 }
 
