@@ -48,8 +48,8 @@
 #define WG_THREADS 128
 #define WG_ITERS (TILE_AMPS / (WG_THREADS * RAMPS))   // register blocks per thread and round (2)
 #define TILE_BLOCK (TILE_THREADS + 128)  // + one warpgroup whose first warp is the copy warp (register re-allocation is per warpgroup)
-#define COMPUTE_REGS 232              // setmaxnreg: 384 x 168 at launch -> 256 x 232 (compute) + 128 x 40 (copy warpgroup)
-#define COPY_REGS 40
+#define COMPUTE_REGS 240              // setmaxnreg: 384 x 168 at launch -> 256 x 240 (compute) + 128 x 24 (copy warpgroup)
+#define COPY_REGS 24
 #define RB 4                          // tile bits held in registers per round
 #define RAMPS (1 << RB)               // amplitudes per register block
 #define TILE_MAX_CHUNKS (1 << (TILE_BITS - TILE_LOW))
@@ -437,6 +437,152 @@ QB_HD void reg_round(cplx* __restrict__ t, const RoundHdr& rd, const TileOp* __r
 #undef OFF
 }
 
+// ------------------------------------------------------------------------------------------
+// The same round with BOTH register blocks of a thread resident (2 x 16 amplitudes): every gate is decoded and
+// dispatched once per thread and round instead of once per block.  Measured (profiles/r2_round_probe_*.txt): decode +
+// indirect branch + operand latency cost ~500 cycles per dispatch against 256 (1-qubit) .. 1024 (2-qubit) cycles of FP64
+// issue per block, so halving the dispatches per amplitude is worth more than the extra registers cost.
+// ------------------------------------------------------------------------------------------
+QB_HD void reg_diag_block(cplx (&v)[RAMPS], unsigned jb, unsigned o0, unsigned o1, unsigned o2, unsigned o3, const TileOp* op, qindex base,
+                          cplx pa, cplx pb, cplx pc, cplx pd, unsigned ok) {
+#define OFF(u) ((((u) & 1) ? o0 : 0u) | (((u) & 2) ? o1 : 0u) | (((u) & 4) ? o2 : 0u) | (((u) & 8) ? o3 : 0u))
+    const int p0 = op->p0, p1 = op->p1, numT = op->numT;
+    const int x0 = (p0 < 0) ? getBit(base, op->e0) : 0;
+    const int x1 = (numT > 1 && p1 < 0) ? getBit(base, op->e1) : 0;
+#pragma unroll
+    for (int u = 0; u < RAMPS; u++) {
+        const unsigned j = jb | OFF(u);
+        const int k0 = (p0 < 0) ? x0 : ((j >> p0) & 1);
+        const int k1 = (numT > 1) ? ((p1 < 0) ? x1 : ((j >> p1) & 1)) : 0;
+        const cplx f = k1 ? (k0 ? pd : pc) : (k0 ? pb : pa);
+        v[u] = csel((ok >> u) & 1, cmul(v[u], f), v[u]);
+    }
+}
+QB_HD void reg_parity_block(cplx (&v)[RAMPS], unsigned jb, unsigned o0, unsigned o1, unsigned o2, unsigned o3, const TileOp* op, qindex base,
+                            cplx pa, cplx pb, unsigned ok) {
+    const unsigned inA = op->inMaskA;
+    const int extPar = parity64((unsigned long long)base & op->extMaskB);
+#pragma unroll
+    for (int u = 0; u < RAMPS; u++) {
+        const int par = (QB_POPC((jb | OFF(u)) & inA) + extPar) & 1;
+        v[u] = csel((ok >> u) & 1, cmul(v[u], par ? pb : pa), v[u]);
+    }
+}
+QB_HD unsigned ctrl_mask_block(unsigned jb, unsigned o0, unsigned o1, unsigned o2, unsigned o3, unsigned cm, unsigned cv) {
+    unsigned ok = 0;
+#pragma unroll
+    for (int u = 0; u < RAMPS; u++) ok |= (unsigned)(((jb | OFF(u)) & cm) == cv) << u;
+    return ok;
+#undef OFF
+}
+
+QB_HD void reg_round2(cplx* __restrict__ t, const RoundHdr& rd, const TileOp* __restrict__ ops, qindex base,
+                      unsigned long long active, const StarTab* __restrict__ tabs, const cplx* __restrict__ starF, int wtid TT_ARGS) {
+    static_assert(WG_ITERS == 2, "the dual-block round driver holds exactly two register blocks per thread");
+    const int b0 = rd.b[0], b1 = rd.b[1], b2 = rd.b[2], b3 = rd.b[3];          // ascending tile-bit positions
+    const unsigned jbA = ins0(ins0(ins0(ins0((unsigned)wtid, b0), b1), b2), b3);
+    const unsigned jbB = ins0(ins0(ins0(ins0((unsigned)(wtid + WG_THREADS), b0), b1), b2), b3);
+    const unsigned o0 = 1u << b0, o1 = 1u << b1, o2 = 1u << b2, o3 = 1u << b3;
+#define OFF(u) ((((u) & 1) ? o0 : 0u) | (((u) & 2) ? o1 : 0u) | (((u) & 4) ? o2 : 0u) | (((u) & 8) ? o3 : 0u))
+    const int first = rd.opBase, num = rd.numOps;
+    const TileOp* op = ops + first;
+    active >>= first;
+
+    // the dispatch quads are fetched two gates ahead; the operands of a gate are fetched when it is dispatched (their
+    // latency is paid once per 32 amplitudes here, and holding a prefetched set for both blocks would cost ~40 registers)
+    int4 d, d1;
+#define LOAD_OPERANDS(q, D, A, B, C_, D_, QA, QB_) do { \
+        if (D.x >= CODE_STAR) { const StarTab& tb_ = tabs[(q)->tab]; A = QB_LDG(&tb_.in[0][jbA & 63]); B = QB_LDG(&tb_.in[1][jbA >> 6]); \
+                                QA = QB_LDG(&tb_.in[0][jbB & 63]); QB_ = QB_LDG(&tb_.in[1][jbB >> 6]); C_ = starF[(q) - ops]; D_ = C_; } \
+        else { A = (q)->m[0]; B = (q)->m[1]; C_ = (q)->m[2]; D_ = (q)->m[3]; QA = A; QB_ = B; } } while (0)
+    d = *reinterpret_cast<const int4*>(op);
+    d1 = d;
+    if (num > 1) d1 = *reinterpret_cast<const int4*>(op + 1);
+
+    cplx vA[RAMPS], vB[RAMPS];
+#pragma unroll
+    for (int u = 0; u < RAMPS; u++) vA[u] = t[jbA | OFF(u)];
+#pragma unroll
+    for (int u = 0; u < RAMPS; u++) vB[u] = t[jbB | OFF(u)];
+    TT_MARK(4);
+
+    for (int o = 0; o < num; o++, op++, active >>= 1) {
+        int4 d2 = d1;
+        if (o + 2 < num) d2 = *reinterpret_cast<const int4*>(op + 2);
+        TT_MARK(10);
+        if (active & 1) {
+            cplx pa, pb, pc, pd, qa, qb;
+            LOAD_OPERANDS(op, d, pa, pb, pc, pd, qa, qb);
+            unsigned okA = 0xFFFFu, okB = 0xFFFFu;
+            const unsigned cm = (unsigned)d.z, cv = (unsigned)d.w;
+            if (cm) { okA = ctrl_mask_block(jbA, o0, o1, o2, o3, cm, cv); okB = ctrl_mask_block(jbB, o0, o1, o2, o3, cm, cv); }
+            switch (d.x) {
+#define D1(L) case CODE_DENSE1 + 2 * L: reg_dense1<L, false>(vA, pa, pb, pc, pd, okA); reg_dense1<L, false>(vB, pa, pb, pc, pd, okB); break; \
+              case CODE_DENSE1 + 2 * L + 1: reg_dense1<L, true>(vA, pa, pb, pc, pd, okA); reg_dense1<L, true>(vB, pa, pb, pc, pd, okB); break;
+            D1(0) D1(1) D1(2) D1(3)
+#undef D1
+#define D2(I, A, B) case CODE_DENSE2 + 2 * I: reg_dense2<A, B, false>(vA, pa, pb, pc, pd, op->m, okA); reg_dense2<A, B, false>(vB, pa, pb, pc, pd, op->m, okB); break; \
+                    case CODE_DENSE2 + 2 * I + 1: reg_dense2<A, B, true>(vA, pa, pb, pc, pd, op->m, okA); reg_dense2<A, B, true>(vB, pa, pb, pc, pd, op->m, okB); break;
+            D2(0, 0, 1) D2(1, 0, 2) D2(2, 0, 3) D2(3, 1, 2) D2(4, 1, 3) D2(5, 2, 3)
+#undef D2
+#define SW(I, A, B) case CODE_SWAP + I: reg_swap<A, B>(vA, okA); reg_swap<A, B>(vB, okB); break;
+            SW(0, 0, 1) SW(1, 0, 2) SW(2, 0, 3) SW(3, 1, 2) SW(4, 1, 3) SW(5, 2, 3)
+#undef SW
+#define PC(X) case CODE_PAULI + X - 1: { const int ep_ = parity64((unsigned long long)base & op->extMaskB); const unsigned lm_ = op->lmaskB, im_ = op->inMaskB; \
+                reg_pauli<X>(vA, lm_, (QB_POPC(jbA & im_) + ep_) & 1, pa, pb, okA); reg_pauli<X>(vB, lm_, (QB_POPC(jbB & im_) + ep_) & 1, pa, pb, okB); } break;
+            PC(1) PC(2) PC(3) PC(4) PC(5) PC(6) PC(7) PC(8) PC(9) PC(10) PC(11) PC(12) PC(13) PC(14) PC(15)
+#undef PC
+            case CODE_DIAG:
+                reg_diag_block(vA, jbA, o0, o1, o2, o3, op, base, pa, pb, pc, pd, okA);
+                reg_diag_block(vB, jbB, o0, o1, o2, o3, op, base, pa, pb, pc, pd, okB);
+                break;
+            case CODE_PARITY:
+                reg_parity_block(vA, jbA, o0, o1, o2, o3, op, base, pa, pb, okA);
+                reg_parity_block(vB, jbB, o0, o1, o2, o3, op, base, pa, pb, okB);
+                break;
+#define ST(L) case CODE_STAR + L: reg_star_bit<L>(vA, cmul(cmul(pa, pb), pc), op->m); reg_star_bit<L>(vB, cmul(cmul(qa, qb), pc), op->m); break; \
+              case CODE_HSTAR + L: reg_hstar_bit<L>(vA, cscale(0.70710678118654752440, cmul(cmul(pa, pb), pc)), op->m); \
+                                   reg_hstar_bit<L>(vB, cscale(0.70710678118654752440, cmul(cmul(qa, qb), pc)), op->m); break;
+            ST(0) ST(1) ST(2) ST(3)
+#undef ST
+            default:            // CODE_STAR + 4: centre outside the round (a tile bit tested through `ok`, or external and set)
+                if (okA) reg_star(vA, cmul(cmul(pa, pb), pc), op->m, okA);
+                if (okB) reg_star(vB, cmul(cmul(qa, qb), pc), op->m, okB);
+                break;
+            }
+        }
+        TT_MARK(11);
+        d = d1; d1 = d2;
+    }
+    TT_MARK(5);
+    // the 32 shared-memory addresses are RE-computed for the stores (an opaque copy of their six ingredients keeps the
+    // compiler from holding 32 address registers live across the whole round, which is what pushed it into spilling)
+    {
+        unsigned sA = jbA, sB = jbB, p0 = o0, p1 = o1, p2 = o2, p3 = o3;
+#ifdef __CUDA_ARCH__
+        asm volatile("" : "+r"(sA), "+r"(sB), "+r"(p0), "+r"(p1), "+r"(p2), "+r"(p3));
+#endif
+#define SOFF(u) ((((u) & 1) ? p0 : 0u) | (((u) & 2) ? p1 : 0u) | (((u) & 4) ? p2 : 0u) | (((u) & 8) ? p3 : 0u))
+#pragma unroll
+        for (int u = 0; u < RAMPS; u++) t[sA | SOFF(u)] = vA[u];
+#pragma unroll
+        for (int u = 0; u < RAMPS; u++) t[sB | SOFF(u)] = vB[u];
+#undef SOFF
+    }
+    TT_MARK(6);
+#undef LOAD_OPERANDS
+#undef OFF
+}
+
+#ifndef QB_DUAL
+#define QB_DUAL 1
+#endif
+#if QB_DUAL
+#define REG_ROUND reg_round2
+#else
+#define REG_ROUND reg_round
+#endif
+
 // shared-memory fallback for the one gate shape that cannot live in a 4-bit register round:
 // Pauli strings with X/Y on more than four tile bits
 QB_HD void smem_pauli(cplx* __restrict__ t, const TileOp& op, qindex base, int wtid) {
@@ -573,7 +719,7 @@ __global__ void __launch_bounds__(TILE_BLOCK, 1) k_tile_pass(cplx* __restrict__ 
         for (int r = 0; r < numRounds; r++) {
             const RoundHdr& rd = rounds[r];
             if (rd.kind == ROUND_REG) {
-                reg_round(t, rd, ops, base, active, tabs, sf, wtid TT_PASS);
+                REG_ROUND(t, rd, ops, base, active, tabs, sf, wtid TT_PASS);
             } else {
                 if ((active >> rd.opBase) & 1) smem_pauli(t, ops[rd.opBase], base, wtid);
                 TT_MARK(7);
@@ -1518,7 +1664,7 @@ static void emulate_pass(std::vector<cplx>& amps, const Emitted& E, int hi) {
         for (int r = 0; r < hdr.numRounds; r++) {
             const RoundHdr& rd = rounds[r];
             for (int wtid = 0; wtid < WG_THREADS; wtid++) {                       // the threads of a round touch disjoint amplitudes
-                if (rd.kind == ROUND_REG) reg_round(t.data(), rd, ops, base, active, tabs, starF, wtid);
+                if (rd.kind == ROUND_REG) REG_ROUND(t.data(), rd, ops, base, active, tabs, starF, wtid);
                 else if ((active >> rd.opBase) & 1) smem_pauli(t.data(), ops[rd.opBase], base, wtid);
             }
         }
@@ -1592,7 +1738,7 @@ __global__ void __launch_bounds__(TILE_THREADS, 1) k_round_probe(const PassHdr* 
     TT_DECL;
     for (int rep = 0; rep < reps; rep++)
         for (int r = 0; r < numRounds; r++) {
-            reg_round(t, rounds[r], ops, 0, ~0ULL, tabs, starF, wtid TT_PASS);
+            REG_ROUND(t, rounds[r], ops, 0, ~0ULL, tabs, starF, wtid TT_PASS);
             wg_sync(wg);
         }
     if (wtid == 0) sink[blockIdx.x * 2 + wg] = t[blockIdx.x & 1023].x;

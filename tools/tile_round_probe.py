@@ -16,7 +16,7 @@ for kind in (2, 1):
             assert rc == 0, rc
             lib.qb_tile_timing_read(buf, 1)
             tot = sum(buf) or 1
-            per = 148 * wgs * 2 * reps * 2 * gates          # SMs x warpgroups x launches(2) x reps x blocks x gates
+            per = 148 * wgs * 2 * reps * 2 * gates          # (dual-block builds dispatch once per two blocks: halve the per-gate slot figures)          # SMs x warpgroups x launches(2) x reps x blocks x gates
             slots = f"prefetch {buf[10] / per:5.0f} clk/gate, dispatch+body {buf[11] / per:5.0f} clk/gate, lds {100 * buf[4] / tot:4.1f}% sts {100 * buf[6] / tot:4.1f}% exit {100 * buf[5] / tot:4.1f}%"
             clk_round = ms.value * 1e-3 * CLK / reps / rounds.value            # per round per warpgroup (2 blocks)
             ideal = gates * (256 if kind == 2 else 128) * 2 * 2 * (wgs)          # DFMA issue cycles per SMSP: instrs x 2 clk x 2 blocks x warps sharing the pipe
