@@ -265,6 +265,12 @@ template <int K, bool CONJ>
 __global__ void __launch_bounds__(128) k_denseK_reg(cplx* __restrict__ amps, qindex numItems, BitIns ins,
                                                     BitList targs, const cplx* __restrict__ matr) {
     constexpr int D = 1 << K;
+    // the matrix is staged in shared memory once per block (conjugated there if asked): every thread then reads each
+    // element with a warp-uniform (broadcast) shared-memory load instead of a global one -- at K = 4 (2-qubit Kraus
+    // superoperators, BASELINE cfg 4) the 256 global loads per thread were what kept the kernel at half its roofline
+    __shared__ cplx sm[D * D];
+    for (int i = threadIdx.x; i < D * D; i += 128) { cplx e = __ldg(&matr[i]); if (CONJ) e.y = -e.y; sm[i] = e; }
+    __syncthreads();
     const qindex n = (qindex)blockIdx.x * 128 + threadIdx.x;
     if (n >= numItems) return;
     const qindex i0 = ins(n);
@@ -276,20 +282,20 @@ __global__ void __launch_bounds__(128) k_denseK_reg(cplx* __restrict__ amps, qin
         for (int b = 0; b < K; b++) o |= (qindex)((j >> b) & 1) << targs.q[b];
         v[j] = amps[i0 | o];
     }
-    // rows are produced one at a time straight from the register copy, so no second buffer is needed
-#pragma unroll 2
-    for (int r = 0; r < D; r++) {
-        cplx acc = mk(0, 0);
+    // rows are produced two at a time straight from the register copy, so no second buffer is needed
+#pragma unroll 1
+    for (int r = 0; r < D; r += (D >= 2 ? 2 : 1)) {
+        cplx acc0 = mk(0, 0), acc1 = mk(0, 0);
 #pragma unroll
         for (int c = 0; c < D; c++) {
-            cplx e = __ldg(&matr[r * D + c]);
-            if (CONJ) e.y = -e.y;
-            acc = cfma(e, v[c], acc);
+            acc0 = cfma(sm[r * D + c], v[c], acc0);
+            if (D >= 2) acc1 = cfma(sm[(r + 1) * D + c], v[c], acc1);
         }
-        qindex o = 0;
+        qindex o0 = 0, o1 = 0;
 #pragma unroll
-        for (int b = 0; b < K; b++) o |= (qindex)((r >> b) & 1) << targs.q[b];
-        amps[i0 | o] = acc;
+        for (int b = 0; b < K; b++) { o0 |= (qindex)((r >> b) & 1) << targs.q[b]; o1 |= (qindex)(((r + 1) >> b) & 1) << targs.q[b]; }
+        amps[i0 | o0] = acc0;
+        if (D >= 2) amps[i0 | o1] = acc1;
     }
 }
 

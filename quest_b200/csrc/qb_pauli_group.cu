@@ -6,7 +6,7 @@
 // high qubits (BASELINE cfg 5: ~9 X/Y sites spread over 28 qubits) cannot enter a shared-memory tile either.
 //
 // But K gadgets with linearly independent masks m_1..m_K only ever mix amplitudes WITHIN the cosets  n ^ span{m_i}
-// of 2^K elements.  So one thread takes a whole coset into registers (16 amplitudes for K = 4), applies the K gadgets
+// of 2^K elements.  So one thread takes a whole coset into registers (32 amplitudes for K = 5), applies the K gadgets
 // one after the other there -- gadget t pairs register g with register g ^ (1 << t) -- and writes the coset back:
 // K gadgets for one read and one write of the state.  Coset representatives are the indices whose K pivot bits (of
 // the masks' echelon form over GF(2)) are zero, enumerated by bit insertion like every other kernel here; consecutive
@@ -64,6 +64,7 @@ __global__ void __launch_bounds__(128) k_pauli_group(cplx* __restrict__ amps, qi
         case 1: if (K > 1) pg_pair<A, (K > 1 ? 1 : 0)>(v, op.c, op.f, par); break;
         case 2: if (K > 2) pg_pair<A, (K > 2 ? 2 : 0)>(v, op.c, op.f, par); break;
         case 3: if (K > 3) pg_pair<A, (K > 3 ? 3 : 0)>(v, op.c, op.f, par); break;
+        case 4: if (K > 4) pg_pair<A, (K > 4 ? 4 : 0)>(v, op.c, op.f, par); break;
         default:                                           // diagonal: v_g *= (parity ? f : c)
 #pragma unroll
             for (int g = 0; g < A; g++) v[g] = cmul(v[g], ((par >> g) & 1u) ? op.f : op.c);
@@ -212,7 +213,8 @@ int qb_pauli_group_apply(const qb_state* q, const PGOp* ops, int numOps, unsigne
     case 1: k_pauli_group<1><<<grid, 128, 0, g_qb.stream>>>((cplx*)q->amps, groups, dev); break;
     case 2: k_pauli_group<2><<<grid, 128, 0, g_qb.stream>>>((cplx*)q->amps, groups, dev); break;
     case 3: k_pauli_group<3><<<grid, 128, 0, g_qb.stream>>>((cplx*)q->amps, groups, dev); break;
-    default: k_pauli_group<4><<<grid, 128, 0, g_qb.stream>>>((cplx*)q->amps, groups, dev); break;
+    case 4: k_pauli_group<4><<<grid, 128, 0, g_qb.stream>>>((cplx*)q->amps, groups, dev); break;
+    default: k_pauli_group<5><<<grid, 128, 0, g_qb.stream>>>((cplx*)q->amps, groups, dev); break;
     }
     QB_LAUNCH_CHECK();
     return 0;
@@ -236,7 +238,8 @@ int qb_pauli_group_expec(const qb_state* q, const unsigned long long* masks, int
     case 1: k_pauli_group_expec<1><<<(unsigned)blocks, QB_BLOCK, 0, g_qb.stream>>>((const cplx*)q->amps, groups, dev, g_qb.redPartials, g_qb.redTicket, devOut); break;
     case 2: k_pauli_group_expec<2><<<(unsigned)blocks, QB_BLOCK, 0, g_qb.stream>>>((const cplx*)q->amps, groups, dev, g_qb.redPartials, g_qb.redTicket, devOut); break;
     case 3: k_pauli_group_expec<3><<<(unsigned)blocks, QB_BLOCK, 0, g_qb.stream>>>((const cplx*)q->amps, groups, dev, g_qb.redPartials, g_qb.redTicket, devOut); break;
-    default: k_pauli_group_expec<4><<<(unsigned)blocks, QB_BLOCK, 0, g_qb.stream>>>((const cplx*)q->amps, groups, dev, g_qb.redPartials, g_qb.redTicket, devOut); break;
+    case 4: k_pauli_group_expec<4><<<(unsigned)blocks, QB_BLOCK, 0, g_qb.stream>>>((const cplx*)q->amps, groups, dev, g_qb.redPartials, g_qb.redTicket, devOut); break;
+    default: k_pauli_group_expec<5><<<(unsigned)blocks, QB_BLOCK, 0, g_qb.stream>>>((const cplx*)q->amps, groups, dev, g_qb.redPartials, g_qb.redTicket, devOut); break;
     }
     QB_LAUNCH_CHECK();
     return 0;

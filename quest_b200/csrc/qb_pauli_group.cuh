@@ -2,7 +2,7 @@
 #pragma once
 #include "qb_common.cuh"
 
-#define PG_K 4                       // independent X/Y masks per pass (2^PG_K amplitudes per thread)
+#define PG_K 5                       // independent X/Y masks per pass (2^PG_K amplitudes per thread: 32 = 128 registers)
 #define PG_AMPS (1 << PG_K)
 #define PG_MAX_OPS 12                // gadgets per pass: PG_K non-diagonal ones plus diagonal ones riding along
 

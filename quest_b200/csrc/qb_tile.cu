@@ -55,6 +55,7 @@
 #define TILE_MAX_CHUNKS (1 << (TILE_BITS - TILE_LOW))
 #define MAX_OPS_PER_PASS 48
 #define QUEUE_MAX 2048                 // deferred gates before a forced flush (cfg 2 issues 680 per step)
+#define PAULI_STREAM_FLUSH 50           // see enqueue(): early flush of pure wide-Pauli streams (a multiple of PG_K)
 #define FUSE_MIN_LOG_AMPS 13          // smaller states use the direct kernels immediately
 #define STAR_SEGS 6                   // external-control tables: 6 segments x 6 bits of the global index
 
@@ -121,7 +122,13 @@ enum { CODE_DENSE1 = 0,      // + 2 * l0 + hasInTileCtrl                (8)
 static inline int pair_index(int a, int b) { return a == 0 ? b - 1 : (a == 1 ? b + 1 : 5); }   // (0,1)(0,2)(0,3)(1,2)(1,3)(2,3) -> 0..5
 
 struct RoundHdr { int kind, opBase, numOps, pad; int b[RB]; };
-struct StarTab { cplx in[2][64]; cplx ext[STAR_SEGS][64]; };
+// phase-star tables: `in` = three 16-entry tables over the 12 tile bits (4 bits each), looked up per thread and block;
+// `ext` = six 64-entry tables over the bits outside the tile, folded into one factor per tile.  The `in` tables of the
+// first STAR_SMEM_SLOTS stars of a pass are copied into shared memory by the kernel (768 bytes each): fetched from
+// global they made the QFT passes wait on L1/L2 (ncu: long_scoreboard 3.5 per issued instruction, profiles/r2_ncu_summary.md)
+#define STAR_SMEM_SLOTS 8
+#define STAR_IN_ENTRIES 48
+struct StarTab { cplx in[3][16]; cplx ext[STAR_SEGS][64]; };
 
 struct PassHdr {
     int numOps, numRounds, numChunks, chunkAmps;
@@ -343,7 +350,7 @@ QB_HD void reg_round(cplx* __restrict__ t, const RoundHdr& rd, const TileOp* __r
     // load sits between two gates -- together with the dispatch quad of gate o+2.
     int4 d, d1; cplx pa, pb, pc, pd;
 #define LOAD_OPERANDS(q, D, A, B, C_, D_) do { \
-        if (D.x >= CODE_STAR) { const StarTab& tb_ = tabs[(q)->tab]; A = QB_LDG(&tb_.in[0][jb & 63]); B = QB_LDG(&tb_.in[1][jb >> 6]); C_ = starF[(q) - ops]; D_ = C_; } \
+        if (D.x >= CODE_STAR) { const StarTab& tb_ = tabs[(q)->tab]; A = QB_LDG(&tb_.in[0][jb & 15]); B = cmul(QB_LDG(&tb_.in[1][(jb >> 4) & 15]), QB_LDG(&tb_.in[2][jb >> 8])); C_ = starF[(q) - ops]; D_ = C_; } \
         else { A = (q)->m[0]; B = (q)->m[1]; C_ = (q)->m[2]; D_ = (q)->m[3]; } } while (0)
     d = *reinterpret_cast<const int4*>(op);
     d1 = d;
@@ -477,7 +484,8 @@ QB_HD unsigned ctrl_mask_block(unsigned jb, unsigned o0, unsigned o1, unsigned o
 }
 
 QB_HD void reg_round2(cplx* __restrict__ t, const RoundHdr& rd, const TileOp* __restrict__ ops, qindex base,
-                      unsigned long long active, const StarTab* __restrict__ tabs, const cplx* __restrict__ starF, int wtid TT_ARGS) {
+                      unsigned long long active, const StarTab* __restrict__ tabs, const cplx* __restrict__ starF, int wtid,
+                      const cplx* __restrict__ starIn TT_ARGS) {
     static_assert(WG_ITERS == 2, "the dual-block round driver holds exactly two register blocks per thread");
     const int b0 = rd.b[0], b1 = rd.b[1], b2 = rd.b[2], b3 = rd.b[3];          // ascending tile-bit positions
     const unsigned jbA = ins0(ins0(ins0(ins0((unsigned)wtid, b0), b1), b2), b3);
@@ -492,8 +500,10 @@ QB_HD void reg_round2(cplx* __restrict__ t, const RoundHdr& rd, const TileOp* __
     // latency is paid once per 32 amplitudes here, and holding a prefetched set for both blocks would cost ~40 registers)
     int4 d, d1;
 #define LOAD_OPERANDS(q, D, A, B, C_, D_, QA, QB_) do { \
-        if (D.x >= CODE_STAR) { const StarTab& tb_ = tabs[(q)->tab]; A = QB_LDG(&tb_.in[0][jbA & 63]); B = QB_LDG(&tb_.in[1][jbA >> 6]); \
-                                QA = QB_LDG(&tb_.in[0][jbB & 63]); QB_ = QB_LDG(&tb_.in[1][jbB >> 6]); C_ = starF[(q) - ops]; D_ = C_; } \
+        if (D.x >= CODE_STAR) { const unsigned sl_ = (unsigned)(q)->pad; \
+                                const cplx* ti_ = (starIn && sl_ < STAR_SMEM_SLOTS) ? starIn + sl_ * STAR_IN_ENTRIES : &tabs[(q)->tab].in[0][0]; \
+                                A = ti_[jbA & 15]; B = cmul(ti_[16 + ((jbA >> 4) & 15)], ti_[32 + (jbA >> 8)]); \
+                                QA = ti_[jbB & 15]; QB_ = cmul(ti_[16 + ((jbB >> 4) & 15)], ti_[32 + (jbB >> 8)]); C_ = starF[(q) - ops]; D_ = C_; } \
         else { A = (q)->m[0]; B = (q)->m[1]; C_ = (q)->m[2]; D_ = (q)->m[3]; QA = A; QB_ = B; } } while (0)
     d = *reinterpret_cast<const int4*>(op);
     d1 = d;
@@ -579,8 +589,10 @@ QB_HD void reg_round2(cplx* __restrict__ t, const RoundHdr& rd, const TileOp* __
 #endif
 #if QB_DUAL
 #define REG_ROUND reg_round2
+#define REG_ROUND_EXTRA(p) , p
 #else
 #define REG_ROUND reg_round
+#define REG_ROUND_EXTRA(p)
 #endif
 
 // shared-memory fallback for the one gate shape that cannot live in a 4-bit register round:
@@ -618,6 +630,7 @@ __global__ void __launch_bounds__(TILE_BLOCK, 1) k_tile_pass(cplx* __restrict__ 
     __shared__ PassHdr hdr;
     __shared__ RoundHdr rounds[MAX_OPS_PER_PASS];
     __shared__ cplx starF[2][2][MAX_OPS_PER_PASS];  // per warpgroup, double-buffered: a fast warp may start its next tile while a slow one finishes
+    __shared__ cplx starIn[STAR_SMEM_SLOTS][STAR_IN_ENTRIES];   // in-tile tables of the pass's first phase stars
 
     const int tid = threadIdx.x;
     for (int i = tid; i < (int)(sizeof(PassHdr) / 4); i += TILE_BLOCK) ((int*)&hdr)[i] = ((const int*)hdrp)[i];
@@ -628,6 +641,12 @@ __global__ void __launch_bounds__(TILE_BLOCK, 1) k_tile_pass(cplx* __restrict__ 
     if (tid == 0) {
         for (int s = 0; s < TILE_STAGES; s++) { mbar_init(&full[s], 1); mbar_init(&done[s], WG_THREADS / 32); }
         asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
+    }
+    __syncthreads();
+    for (int o = 0; o < numOps; o++) {                 // (ops[] is in shared memory by now)
+        const unsigned sl = (unsigned)ops[o].pad;
+        if ((ops[o].kind == OP_STAR || ops[o].kind == OP_HSTAR) && sl < STAR_SMEM_SLOTS && tid < STAR_IN_ENTRIES)
+            starIn[sl][tid] = __ldg(&tabs[ops[o].tab].in[0][0] + tid);
     }
     __syncthreads();
 
@@ -719,7 +738,7 @@ __global__ void __launch_bounds__(TILE_BLOCK, 1) k_tile_pass(cplx* __restrict__ 
         for (int r = 0; r < numRounds; r++) {
             const RoundHdr& rd = rounds[r];
             if (rd.kind == ROUND_REG) {
-                REG_ROUND(t, rd, ops, base, active, tabs, sf, wtid TT_PASS);
+                REG_ROUND(t, rd, ops, base, active, tabs, sf, wtid REG_ROUND_EXTRA(&starIn[0][0]) TT_PASS);
             } else {
                 if ((active >> rd.opBase) & 1) smem_pauli(t, ops[rd.opBase], base, wtid);
                 TT_MARK(7);
@@ -941,6 +960,7 @@ static void emit_pass(const qb_state* q, const std::vector<QOp>& ops, const Pass
     order_rounds(ops, pass, S, reorder, order, roundLen, roundKind);
 
     std::vector<unsigned> needIn;            // per op: tile-bit positions its non-diagonal targets occupy
+    unsigned long long numStars = 0;
     for (int idx : order) {
         const QOp& o = ops[idx];
         TileOp t; memset(&t, 0, sizeof t);
@@ -961,13 +981,14 @@ static void emit_pass(const qb_state* q, const std::vector<QOp>& ops, const Pass
         case OP_STAR: case OP_HSTAR: {
             t.p0 = pos[o.t0]; t.e0 = o.t0;
             StarTab tb;
-            long double angIn[2][64] = {{0}}, angExt[STAR_SEGS][64] = {{0}};
+            long double angIn[3][16] = {{0}}, angExt[STAR_SEGS][64] = {{0}};
             for (auto& ce : o.star) {
                 int c = ce.first; long double th = ce.second;
-                if (pos[c] >= 0) { int p = pos[c]; for (int v = 0; v < 64; v++) if ((v >> (p % 6)) & 1) angIn[p / 6][v] += th; }
+                if (pos[c] >= 0) { int p = pos[c]; for (int v = 0; v < 16; v++) if ((v >> (p % 4)) & 1) angIn[p / 4][v] += th; }
                 else { for (int v = 0; v < 64; v++) if ((v >> (c % 6)) & 1) angExt[c / 6][v] += th; }
             }
-            for (int s = 0; s < 2; s++) for (int v = 0; v < 64; v++) tb.in[s][v] = mk((double)cosl(angIn[s][v]), (double)sinl(angIn[s][v]));
+            for (int s = 0; s < 3; s++) for (int v = 0; v < 16; v++) tb.in[s][v] = mk((double)cosl(angIn[s][v]), (double)sinl(angIn[s][v]));
+            t.pad = numStars++;              // shared-memory slot of its in-tile tables (the kernel keeps the first STAR_SMEM_SLOTS)
             for (int s = 0; s < STAR_SEGS; s++) for (int v = 0; v < 64; v++) tb.ext[s][v] = mk((double)cosl(angExt[s][v]), (double)sinl(angExt[s][v]));
             t.tab = (int)E.tabs.size();
             E.tabs.push_back(tb);
@@ -1133,27 +1154,36 @@ static void plan_passes(std::vector<QOp>& ops, bool reorder, std::vector<QOp>& m
     for (size_t i = 0; i < merged.size(); i++) remaining[i] = (int)i;
     while (!remaining.empty()) {
         Pass cur;
-        if (__builtin_popcountll(highNeed(merged[remaining[0]])) > maxHigh) {
+        {
             // A Pauli string with X/Y on more than six high qubits fits no tile.  It and the control-free Pauli / parity
-            // gadgets that follow it in program order (Trotter circuits are nothing else) share ONE pass as long as
-            // their X/Y masks stay linearly independent: they only mix amplitudes within cosets of the masks' span
-            unsigned long long masks[PG_K]; int nm = 0; size_t take = 0;
-            for (; take < remaining.size() && take < PG_MAX_OPS; take++) {
-                const QOp& o = merged[remaining[take]];
-                if (o.ctrlMask || (o.kind != OP_PAULI && o.kind != OP_PARITY)) break;
-                if (o.kind == OP_PAULI) {
-                    if (nm == PG_K) break;
-                    masks[nm] = o.maskA;
-                    if (pg_rank(masks, nm + 1, nullptr) != nm + 1) break;
-                    nm++;
+            // gadgets around it in program order (Trotter circuits are nothing else) share ONE pass as long as their
+            // X/Y masks stay linearly independent: they only mix amplitudes within cosets of the masks' span.  A group
+            // is formed when it starts with a control-free Pauli string and holds at least one string that fits no tile
+            // (narrow strings between wide ones ride along instead of costing a pass of their own).
+            const QOp& head = merged[remaining[0]];
+            const bool headWide = __builtin_popcountll(highNeed(head)) > maxHigh;
+            unsigned long long masks[PG_K]; int nm = 0; size_t take = 0; bool anyWide = false;
+            if (head.kind == OP_PAULI && !head.ctrlMask)
+                for (; take < remaining.size() && take < PG_MAX_OPS; take++) {
+                    const QOp& o = merged[remaining[take]];
+                    if (o.ctrlMask || (o.kind != OP_PAULI && o.kind != OP_PARITY)) break;
+                    if (o.kind == OP_PAULI) {
+                        if (nm == PG_K) break;
+                        masks[nm] = o.maskA;
+                        if (pg_rank(masks, nm + 1, nullptr) != nm + 1) break;
+                        nm++;
+                        anyWide |= __builtin_popcountll(highNeed(o)) > maxHigh;
+                    }
                 }
+            const bool group = take >= 2 && anyWide;
+            if (group || headWide) {
+                if (!group) take = 1;
+                cur.opIdx.assign(remaining.begin(), remaining.begin() + take);
+                cur.high = group ? PASS_PGROUP : PASS_DIRECT;
+                remaining.erase(remaining.begin(), remaining.begin() + take);
+                passes.push_back(cur);
+                continue;
             }
-            if (take < 2) take = 1;
-            cur.opIdx.assign(remaining.begin(), remaining.begin() + take);
-            cur.high = take >= 2 ? PASS_PGROUP : PASS_DIRECT;
-            remaining.erase(remaining.begin(), remaining.begin() + take);
-            passes.push_back(cur);
-            continue;
         }
         std::vector<int> rest;
         first_fit(merged, remaining, reorder ? MAX_OPS_PER_PASS : 1000000, [&](const QOp& o, bool) {
@@ -1364,6 +1394,17 @@ static int enqueue(const qb_state* q, QOp& o) {
     }
     sq->ops.push_back(o);
     if (sq->ops.size() >= QUEUE_MAX) s_status = flush_one(*sq);
+    // Trotter-like streams (nothing but control-free Pauli / phase gadgets): the planner groups them four per pass in
+    // program order, so a longer queue buys no better plan -- start executing every PAULI_STREAM_FLUSH gadgets, so that
+    // the device works while the host is still issuing the rest (the API's per-gadget host cost is ~0.15 ms)
+    else if (sq->ops.size() >= PAULI_STREAM_FLUSH && sq->ops.size() % PAULI_STREAM_FLUSH == 0) {
+        bool stream = true;
+        for (size_t i = sq->ops.size() - PAULI_STREAM_FLUSH; i < sq->ops.size() && stream; i++) {
+            const QOp& g = sq->ops[i];
+            stream = !g.ctrlMask && (g.kind == OP_PARITY || g.kind == OP_PAULI);
+        }
+        if (stream && sq->ops.size() == PAULI_STREAM_FLUSH) s_status = flush_one(*sq);
+    }
     return 1;
 }
 
@@ -1664,7 +1705,7 @@ static void emulate_pass(std::vector<cplx>& amps, const Emitted& E, int hi) {
         for (int r = 0; r < hdr.numRounds; r++) {
             const RoundHdr& rd = rounds[r];
             for (int wtid = 0; wtid < WG_THREADS; wtid++) {                       // the threads of a round touch disjoint amplitudes
-                if (rd.kind == ROUND_REG) REG_ROUND(t.data(), rd, ops, base, active, tabs, starF, wtid);
+                if (rd.kind == ROUND_REG) REG_ROUND(t.data(), rd, ops, base, active, tabs, starF, wtid REG_ROUND_EXTRA(nullptr));
                 else if ((active >> rd.opBase) & 1) smem_pauli(t.data(), ops[rd.opBase], base, wtid);
             }
         }
@@ -1738,7 +1779,7 @@ __global__ void __launch_bounds__(TILE_THREADS, 1) k_round_probe(const PassHdr* 
     TT_DECL;
     for (int rep = 0; rep < reps; rep++)
         for (int r = 0; r < numRounds; r++) {
-            REG_ROUND(t, rounds[r], ops, 0, ~0ULL, tabs, starF, wtid TT_PASS);
+            REG_ROUND(t, rounds[r], ops, 0, ~0ULL, tabs, starF, wtid REG_ROUND_EXTRA(nullptr) TT_PASS);
             wg_sync(wg);
         }
     if (wtid == 0) sink[blockIdx.x * 2 + wg] = t[blockIdx.x & 1023].x;
