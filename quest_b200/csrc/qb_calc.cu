@@ -368,7 +368,7 @@ static int pauliGrouped(const qb_state* q, const unsigned long long* masks, int 
             if (!cur.empty()) groups.push_back(cur);
             cur.assign(1, t); curMasks[0] = xy;
         }
-        if ((int)cur.size() == PG_K) { groups.push_back(cur); cur.clear(); }
+        if ((int)cur.size() == PG_K_EXPEC) { groups.push_back(cur); cur.clear(); }
     }
     if (!cur.empty()) groups.push_back(cur);
     // several groups per host synchronisation: each writes its 2k doubles to its own slot of the result area
