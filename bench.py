@@ -289,12 +289,12 @@ class Product:
         return q
 
     def stats(self):
-        s = (C.c_double * 6)()
+        s = (C.c_double * 8)()
         self.lib.qb_tile_stats(s)
         a, b = C.c_ulonglong(), C.c_ulonglong()
         self.lib.qb_p2p_stats(C.byref(a), C.byref(b))
         return {"launches": self.lib.qb_launch_count(), "passes": s[0], "rounds": s[1], "tile_ops": s[2], "direct_ops": s[3],
-                "fma": s[5], "exchanges": a.value, "link_bytes": b.value}
+                "fma": s[5], "pass_bytes": s[6], "exchanges": a.value, "link_bytes": b.value}
 
     def gate(self, q, op, m=None):
         Q = self.Q
@@ -563,7 +563,8 @@ def run_product(args, rank, world, local_rank):
     passes = (s1["passes"] + s1["direct_ops"] - s0["passes"] - s0["direct_ops"]) / args.steps
     kernel_launches = launches / args.steps
     achieved = bytes_step / (ms_per_step * 1e-3) / 1e9
-    physical = kernel_launches * 2 * AMP_BYTES * local_amps / (ms_per_step * 1e-3) / 1e9
+    # bytes the gate passes streamed (the backend counts them per launch: tiles x 128 KiB, halves for restricted passes)
+    physical = (s1["pass_bytes"] - s0["pass_bytes"]) / args.steps / (ms_per_step * 1e-3) / 1e9
     fp64 = 2 * (s1["fma"] - s0["fma"]) / args.steps / (ms_per_step * 1e-3) / 1e12
     roofline = {"kernel": "k_tile_pass (fused multi-gate pass over the shard; >95% of the step's device time) + the few direct single-gate kernels",
                 "bound": "hbm", "achieved": achieved, "peak": peak_gbs, "unit": "GB/s", "frac": achieved / peak_gbs,

@@ -102,8 +102,9 @@ unsigned long long qb_launch_count(void);                /* kernels launched by 
 int         qb_set_tile_engine(int enabled);             /* 1 (default): fused TMA tile passes (gate absorption + commuting re-order); 2: fused, program order; 0: direct kernels only */
 /* cumulative statistics of the deferred-gate engine since load: out[0] fused tile passes launched, [1] register rounds
  * in them, [2] gates executed inside tile passes, [3] gates run as direct kernels, [4] gates received by the queues,
- * [5] FP64 fused multiply-adds executed for them (bench.py derives the FP64-pipe fraction of the roofline from it) */
-int         qb_tile_stats(double out[6]);
+ * [5] FP64 fused multiply-adds executed for them (bench.py derives the FP64-pipe fraction of the roofline from it),
+ * [6] bytes those passes streamed through HBM (read + write of the amplitudes they touch), [7] reserved */
+int         qb_tile_stats(double out[8]);
 
 /* ------------------------------------------------------------------------------------------
  * getters / setters                          (gpu_subroutines.hpp:24-36)

@@ -89,6 +89,7 @@ static unsigned long long s_flushEpoch = 0;       // bumped whenever a non-empty
 // cumulative execution statistics (qb_tile_stats): what the planner made of the gates it was given
 static unsigned long long s_statPasses = 0, s_statRounds = 0, s_statTileOps = 0, s_statDirectOps = 0, s_statQueuedGates = 0;
 static double s_statFmaAmps = 0;                   // FP64 fused multiply-adds issued per pass, summed: ops x amplitudes x FMA per amplitude
+static double s_statPassBytes = 0;                 // bytes the launched passes stream through HBM (read + write of what they touch)
 // Restricted flush (qb_tile_flush_restricted): the queue is applied only to the amplitudes whose index bits `mask`
 // hold `vals` -- as if every queued gate carried those extra controls, but without disturbing gate absorption or the
 // phase-star merge (the restriction is a property of the passes: whole tiles are pruned).  Used to overlap a
@@ -1281,7 +1282,9 @@ static int flush_one(StateQueue& sq) {
         attrSet = true;
     }
     for (size_t i = 0; i < passKind.size() && !rc; i++) {
+        const double shardBytes = 2.0 * sizeof(cplx) * (double)q.numAmpsPerNode / (double)(1ULL << __builtin_popcountll(s_restrictMask));
         if (passKind[i] == -2) {              // coset-blocked Pauli pass
+            s_statPassBytes += shardBytes;
             const Pass& pp = passes[passArg[i]];
             PGOp gops[PG_MAX_OPS]; int ng = 0;
             for (int idx : pp.opIdx) {
@@ -1295,9 +1298,11 @@ static int flush_one(StateQueue& sq) {
             s_statPasses++; s_statTileOps += ng;
             continue;
         }
-        if (passKind[i] < 0) { rc = run_direct(&q, merged[passArg[i]]); s_statDirectOps++; s_statFmaAmps += fma_per_amp(merged[passArg[i]]) * (double)q.numAmpsPerNode; continue; }
+        if (passKind[i] < 0) { s_statPassBytes += shardBytes / (double)(1ULL << __builtin_popcountll(merged[passArg[i]].ctrlMask)) * (merged[passArg[i]].kind == OP_SWAP ? 0.5 : 1.0);
+                               rc = run_direct(&q, merged[passArg[i]]); s_statDirectOps++; s_statFmaAmps += fma_per_amp(merged[passArg[i]]) * (double)q.numAmpsPerNode; continue; }
         const int hi = passKind[i];
         s_statPasses++; s_statRounds += E.hdrs[hi].numRounds; s_statTileOps += E.hdrs[hi].numOps;
+        s_statPassBytes += 2.0 * sizeof(cplx) * (double)TILE_AMPS * (double)E.hdrs[hi].numTiles;
         const PassHdr* dh = (const PassHdr*)s_devDesc + hi;
         const RoundHdr* dr = (const RoundHdr*)(s_devDesc + bh) + E.roundBase[hi];
         const TileOp* dops = (const TileOp*)(s_devDesc + bh + br) + E.opBase[hi];
@@ -1336,9 +1341,11 @@ extern "C" int qb_queue_info(const qb_state* q, unsigned long long* touchedSuffi
 
 // cumulative planner / execution statistics since the library was loaded:
 // out[0] tile passes launched, [1] rounds in them, [2] ops executed inside tile passes, [3] ops run as direct kernels,
-// [4] gates received by the queue, [5] FP64 fused multiply-adds executed for them (thread-level count)
-extern "C" int qb_tile_stats(double out[6]) {
+// [4] gates received by the queue, [5] FP64 fused multiply-adds executed for them (thread-level count),
+// [6] bytes those passes and kernels streamed through HBM (what they read + wrote), [7] reserved
+extern "C" int qb_tile_stats(double out[8]) {
     if (!out) return -1;
+    out[6] = s_statPassBytes; out[7] = 0;
     out[0] = (double)s_statPasses; out[1] = (double)s_statRounds; out[2] = (double)s_statTileOps; out[3] = (double)s_statDirectOps;
     out[4] = (double)s_statQueuedGates; out[5] = s_statFmaAmps;
     return 0;

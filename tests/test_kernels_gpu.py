@@ -695,7 +695,7 @@ def test_interleaved_states_keep_fusing(n):
     rng = np.random.default_rng(2300 + n)
     sts = [rand_sv(rng, n) for _ in range(3)]
     devs = [Dev(s) for s in sts]
-    stats0 = (C.c_double * 6)(); capi.call("qb_tile_stats", stats0)
+    stats0 = (C.c_double * 8)(); capi.call("qb_tile_stats", stats0)
     launches0 = capi.lib().qb_launch_count()
     nops = 60
     for _ in range(nops):
@@ -703,7 +703,7 @@ def test_interleaved_states_keep_fusing(n):
             _random_fusable_op(rng, n, s, d)
     errs = [rel_l2(d.host(), s.amps) for s, d in zip(sts, devs)]
     launches = capi.lib().qb_launch_count() - launches0
-    stats1 = (C.c_double * 6)(); capi.call("qb_tile_stats", stats1)
+    stats1 = (C.c_double * 8)(); capi.call("qb_tile_stats", stats1)
     assert max(errs) <= TOL * 5, f"interleaved states: rel-L2 {errs}"
     assert launches < nops, f"switching states flushed the queues: {launches} launches for 3 x {nops} gates"
     assert stats1[4] - stats0[4] >= 3 * nops * 0.9 and stats1[0] > stats0[0]
