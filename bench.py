@@ -329,6 +329,7 @@ class Product:
 
 
 def secondary_configs(P, n_local, full):
+    torch = P.torch
     """the other BASELINE configurations, through the public API, device-timed (events) incl. the final syncQuESTEnv"""
     from quest_b200.program import _Interp
     from tests import programs as TP
@@ -345,20 +346,35 @@ def secondary_configs(P, n_local, full):
             out[f"cfg3_{n3}q"] = {"error": str(exc)[:200]}
             continue
         ops = P.mats(cfg3_stream(n3))
+        reps = 2
+        evs = [[torch.cuda.Event(enable_timing=True) for _ in range(4)] for _ in range(reps)]
 
-        def circuit():
+        def circuit(ev=None):
+            if ev: ev[0].record()
             Q.initPlusState(q)
+            if ev: ev[1].record()
             for op, m in ops:
                 P.gate(q, op, m)
-            Q.syncQuESTEnv()
+            P.capi.call("qb_flush")
+            if ev: ev[2].record()
+            Q.syncQuESTEnv()                    # restores the canonical qubit order (exchanges, when rank bits were relabelled)
+            if ev: ev[3].record()
+        circuit()
+        P.barrier()
         s0 = P.stats()
-        ms = P.timed(circuit, 2, 1)
+        for r in range(reps):
+            circuit(evs[r])
+        P.barrier()
         s1 = P.stats()
+        ms = P.max_over_ranks(sum(e[0].elapsed_time(e[3]) for e in evs) / reps)
+        ms_gates = P.max_over_ranks(sum(e[1].elapsed_time(e[2]) for e in evs) / reps)
+        ms_restore = P.max_over_ranks(sum(e[2].elapsed_time(e[3]) for e in evs) / reps)
         prob = Q.calcTotalProb(q)
         Q.destroyQureg(q)
         out[f"cfg3_{n3}q"] = {"workload": f"cfg3: {n3}q random circuit (100 gates from {{H,Rx,CompMatr1,CNOT,CompMatr2}}, seed 34008) incl. initPlusState + syncQuESTEnv",
-                              "n_gpus": world, "ms_per_circuit": ms, "circuit_gates_per_s": 100 / (ms * 1e-3), "exchanges_per_circuit": (s1["exchanges"] - s0["exchanges"]) / 3,
-                              "link_bytes_per_dir_per_circuit": (s1["link_bytes"] - s0["link_bytes"]) / 3, "launches_per_circuit": (s1["launches"] - s0["launches"]) / 3,
+                              "n_gpus": world, "ms_per_circuit": ms, "gates_ms": ms_gates, "restore_canonical_order_ms": ms_restore,
+                              "circuit_gates_per_s": 100 / (ms * 1e-3), "exchanges_per_circuit": (s1["exchanges"] - s0["exchanges"]) / reps,
+                              "link_bytes_per_dir_per_circuit": (s1["link_bytes"] - s0["link_bytes"]) / reps, "launches_per_circuit": (s1["launches"] - s0["launches"]) / reps,
                               "total_prob": prob}
 
     def run_prog(prog, reps):
@@ -457,6 +473,7 @@ def run_product(args, rank, world, local_rank):
 
     # ---------------- device-resident timing ----------------
     Q.initPlusState(qureg)
+    Q.syncQuESTEnv()
     timed_steps(step, args.warmup)
     sampler = ClockSampler(local_rank)
     if rank == 0:
@@ -477,8 +494,10 @@ def run_product(args, rank, world, local_rank):
             circuit()
             return Q.calcProbOfQubitOutcome(qureg, n - 1, 0)       # device -> host read of the step's result
 
-        Q.initPlusState(qureg) if cfg3 else Q.initZeroState(qureg)
-        for _ in range(min(args.warmup, 2)):
+        # same starting point as the device-timed loop (fresh state, identity qubit map, W warm-up steps): with lazy
+        # relabelling the number of exchanges a step needs depends on the steps before it
+        Q.initPlusState(qureg)
+        for _ in range(args.warmup):
             e2e_step()
         Q.syncQuESTEnv()
         P.barrier()
