@@ -718,7 +718,7 @@ def _wide_pauli(rng, n, min_sites=8):
     return x, y, z
 
 
-@pytest.mark.parametrize("n", [13, 16, 19, 22])
+@pytest.mark.parametrize("n", [13, 16, 19, 21])
 def test_wide_pauli_gadgets_share_passes(n):
     """Trotter-like streams: control-free Pauli gadgets on many high qubits, interleaved with Z-only phase gadgets and
     the occasional repeated (linearly dependent) string.  The engine runs them PG_K at a time through the coset-blocked
