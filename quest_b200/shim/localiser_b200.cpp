@@ -231,7 +231,7 @@ static bool overlapEnabled() {
 
 static int overlapMinGates() {
     static int n = -1;
-    if (n < 0) { const char* e = std::getenv("QUEST_B200_OVERLAP_MIN_GATES"); n = e ? std::atoi(e) : 16; if (n < 1) n = 1; }
+    if (n < 0) { const char* e = std::getenv("QUEST_B200_OVERLAP_MIN_GATES"); n = e ? std::atoi(e) : 400; if (n < 1) n = 1; }
     return n;
 }
 
@@ -379,9 +379,11 @@ static bool pullTargetsIntoShard(Qureg qureg, QubitMap& m, vector<int>& targs, c
 
         // gates are waiting and none of them involves the victim: exchange through the buffers on a second stream while
         // they run on the half that stays (every rank takes this branch together: the test uses rank-independent state)
-        // Overlapping drains the queue (in two halves), which shortens the planner's fusion window, so it pays only when
-        // enough work is waiting to hide the ~11 ms transfer behind (measured: profiles/r2_overlap_trace_2gpu.txt);
-        // smaller queues are overtaken instead and keep growing
+        // Overlapping drains the queue (in two halves), which shortens the planner's fusion window and cuts gate
+        // absorption short, so it pays only when a LOT of work is waiting to hide the ~11 ms transfer behind (the trace in
+        // profiles/r2_overlap_trace_2gpu.txt; cfg 2 on 8 GPUs: 1032 ms per step without overlap, 939 ms overlapping every
+        // queue of >= 8 gates, 888 ms overlapping only QFT-sized queues -- profiles/r2_bench_8gpu_overlap_variants.txt);
+        // smaller queues are overtaken instead (qb_p2p_swapHalvesDeferred) and keep growing
         auto qg = g_queuedGates.find(qureg.gpuAmps);
         bool overlap = mayOvertake && overlapEnabled() && queued && !((touched >> victim) & 1)
                     && qureg.gpuCommBuffer != nullptr && victim >= 10
