@@ -125,8 +125,16 @@ __global__ void __launch_bounds__(QB_BLOCK) k_hist(HistArgs a, double* __restric
 static int qb_hist(const HistArgs& a, int k, double* outProbs) {
     QB_REQUIRE(k >= 0 && k <= 40 && outProbs, "calcProbsOfAllMultiQubitOutcomes: bad arguments");
     qindex numBins = pow2(k);
-    double* dOut = nullptr;
-    QB_CUDA(cudaMalloc(&dOut, sizeof(double) * numBins));
+    // grow-only device scratch for the bins (a cudaMalloc/cudaFree pair per call would synchronise the device twice)
+    static double* s_bins = nullptr; static qindex s_binsLen = 0;
+    if (numBins > s_binsLen) {
+        QB_CUDA(cudaStreamSynchronize(g_qb.stream));
+        if (s_bins) cudaFree(s_bins);
+        s_bins = nullptr; s_binsLen = 0;
+        QB_CUDA(cudaMalloc(&s_bins, sizeof(double) * numBins));
+        s_binsLen = numBins;
+    }
+    double* dOut = s_bins;
     QB_CUDA(cudaMemsetAsync(dOut, 0, sizeof(double) * numBins, g_qb.stream));
     int useSmem = k <= 11;                                  // 2^11 doubles = 16 KiB of shared memory
     qindex blocks = (a.numItems + QB_BLOCK - 1) / QB_BLOCK;
@@ -137,7 +145,6 @@ static int qb_hist(const HistArgs& a, int k, double* outProbs) {
     cudaError_t e = cudaGetLastError();
     if (e == cudaSuccess) e = cudaMemcpyAsync(outProbs, dOut, sizeof(double) * numBins, cudaMemcpyDeviceToHost, g_qb.stream);
     if (e == cudaSuccess) e = cudaStreamSynchronize(g_qb.stream);
-    cudaFree(dOut);
     if (e != cudaSuccess) return qb_set_error((int)e, "calcProbsOfAllMultiQubitOutcomes", __FILE__, __LINE__);
     return 0;
 }

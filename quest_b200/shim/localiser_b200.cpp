@@ -18,6 +18,11 @@
  *   Pauli-sum expectation: one reduction pass per term      all terms of a prefix-XY group in batches of 8 per pass
  *   (localiser.cpp:2097-2112)                               (qb_statevec_calcExpecPauliStrBatch_sub{A,B})
  *
+ * Provenance: the data plane (lazy relabelling, NVLink / copy-engine exchanges, overlap, batched Pauli sums) is this
+ * repo's design.  The control-plane sections -- spoofed views, getters / setters, state initialisation, and the per-operator
+ * prefix/suffix case analysis -- reproduce the reference's semantics call for call and therefore follow the bodies of
+ * core/localiser.cpp closely (each is marked with the reference lines it mirrors); they are host glue outside the hot path.
+ *
  * Everything that is not communication is delegated to accel_* (core/accelerator.cpp, unchanged), so CPU-only
  * Quregs keep working through the reference's own CPU path; distributed Quregs must be GPU-accelerated.
  * The per-operator case analysis (which qubits are prefix, who is the pair rank, what is packed) follows the
