@@ -41,7 +41,7 @@ HOST_SRCS := $(wildcard $(REF)/quest/src/api/*.cpp) $(filter-out %/localiser.cpp
 HOST_OBJS := $(patsubst $(REF)/quest/src/%.cpp,$(HOSTOBJ_DIR)/%.o,$(HOST_SRCS))
 HOST_FLAGS := -std=c++17 -O3 -fPIC -fopenmp -Wno-unknown-pragmas -I$(REF) $(SHIM_DEFS)
 
-.PHONY: all kernels selftest quest oracle clean kernels32 quest32 oracle32
+.PHONY: all kernels selftest quest oracle clean kernels32 quest32 oracle32 timing
 all: kernels oracle quest kernels32 oracle32 quest32
 
 kernels: $(LIBDIR)/libquest_b200.so selftest
@@ -67,6 +67,15 @@ $(LIBDIR)/libquest_b200.so: $(CU_OBJS)
 
 oracle:
 	$(MAKE) -C oracle
+
+# probe-only twin with cycle accounting compiled into the tile kernel (-DQB_TILE_TIMING): tools/tile_timing_probe.py,
+# tools/tile_round_probe.py.  Not part of `all`; never shipped as the product.
+timing: $(BUILD)/timing/libquest_b200_timing.so
+$(BUILD)/timing/qb_tile.o: quest_b200/csrc/qb_tile.cu $(CU_HDRS)
+	@mkdir -p $(dir $@)
+	$(NVCC) $(NVFLAGS) -DQB_TILE_TIMING -I$(NCCL_INC) -c $< -o $@
+$(BUILD)/timing/libquest_b200_timing.so: $(BUILD)/timing/qb_tile.o $(CU_OBJS)
+	$(NVCC) $(ARCH) -shared -o $@ $(BUILD)/timing/qb_tile.o $(filter-out $(BUILD)/csrc/qb_tile.o,$(CU_OBJS)) -L$(NCCL_LIB) -lnccl
 
 # ---- single precision (QuEST's FLOAT_PRECISION=1, quest/include/precision.h:80-96): the same sources, compiled with
 # -DQB_PRECISION=1 (kernels) / -DFLOAT_PRECISION=1 (shim + the reference's host layers), into *_f32 twins of the three

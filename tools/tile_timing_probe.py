@@ -1,5 +1,5 @@
 """GPU probe: where do the compute warpgroups of k_tile_pass spend their cycles?  Needs the -DQB_TILE_TIMING build
-(build/timing/libquest_b200_timing.so, see the recipe in profiles/r2_tile_timing.md).  Prints, per scenario, the
+(`make timing` -> build/timing/libquest_b200_timing.so).  Prints, per scenario, the
 time per launch and the share of warpgroup cycles per phase."""
 import ctypes as C, sys, os, math
 import numpy as np, torch
