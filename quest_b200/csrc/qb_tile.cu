@@ -1356,6 +1356,9 @@ extern "C" int qb_tile_stats(double out[8]) {
 int qb_tile_flush_restricted(const qb_state* q, unsigned long long mask, unsigned long long vals, bool keepQueue) {
     StateQueue* sq = find_queue(q);
     if (!sq || sq->ops.empty() || s_inFlush) return 0;
+    // a restriction is realised by pruning whole tiles, so its bits must lie outside every tile: not among the low
+    // TILE_LOW index bits, which belong to all tiles
+    if (mask & ((1ULL << TILE_LOW) - 1)) return qb_set_error(-1, "restricted flush: restricted bits must be >= 6", __FILE__, __LINE__);
     for (const QOp& o : sq->ops)
         if ((nonDiagTargets(o) | diagQubits(o)) & mask) return qb_set_error(-1, "restricted flush: a queued gate involves a restricted bit", __FILE__, __LINE__);
     StateQueue work = *sq;
@@ -1759,6 +1762,76 @@ extern "C" int qb_selftest_tile_emulation(int numQubits, int numOps, unsigned se
     if (maxErr) *maxErr = norm > 0 ? err / norm : err;
     if (numTilePasses) *numTilePasses = tilePasses;
     if (numDirectOps) *numDirectOps = directOps;
+    return 0;
+}
+
+// ------------------------------------------------------------------------------------------
+// host check of the RESTRICTED flush that the exchange / compute overlap is built on (qb_tile_flush_restricted,
+// qb_p2p_swapHalvesOverlapped): a random gate list that never touches index bit `bit` is planned and emulated twice,
+// once restricted to bit == 0 and once to bit == 1 -- the two halves of a shard that meet the gates at different
+// times -- and the result must equal plain application of the list to the whole state.  Also checks that every
+// restricted pass really skips the other half (numTiles halves) and that gate absorption and the phase-star merge,
+// which extra per-gate controls would have disabled, still take place (numOpsPlanned < numOps).
+// ------------------------------------------------------------------------------------------
+extern "C" int qb_selftest_restricted_flush(int numQubits, int numOps, unsigned seed, int bit, double* maxErr, int* numTilePasses, int* numOpsPlanned) {
+    if (numQubits < TILE_BITS + 1 || numQubits > 20 || numOps < 1 || bit < 0 || bit >= numQubits) return -1;
+    if (bit < TILE_LOW) return -5;                 // same precondition as qb_tile_flush_restricted
+    std::mt19937_64 rng(seed);
+    auto unif = [&]() { return (double)(rng() >> 11) * (1.0 / 9007199254740992.0); };
+    const int n = numQubits;
+    // random ops on n-1 qubits, then re-labelled so that index bit `bit` is never involved
+    std::vector<QOp> ops;
+    selftest_random_ops(n - 1, numOps, rng, ops);
+    auto spread = [&](unsigned long long m) { const unsigned long long lo = m & ((1ULL << bit) - 1); return ((m >> bit) << (bit + 1)) | lo; };
+    auto qb = [&](int t) { return t >= bit ? t + 1 : t; };
+    for (QOp& o : ops) {
+        o.ctrlMask = spread(o.ctrlMask); o.ctrlVals = spread(o.ctrlVals); o.maskA = spread(o.maskA); o.maskB = spread(o.maskB);
+        o.t0 = qb(o.t0); o.t1 = qb(o.t1);
+        for (auto& ce : o.star) ce.first = qb(ce.first);
+    }
+    qb_state q; memset(&q, 0, sizeof q); q.numAmpsPerNode = 1LL << n; q.logNumAmpsPerNode = n; q.numQubits = n;
+    std::vector<hc> ref((size_t)1 << n);
+    for (auto& v : ref) v = hc(2 * unif() - 1, 2 * unif() - 1);
+    std::vector<cplx> state(ref.size());
+    for (size_t i = 0; i < ref.size(); i++) state[i] = mk(ref[i].real(), ref[i].imag());
+    for (const QOp& o : ops) host_apply(ref, o);
+
+    int tilePasses = 0, planned = 0, rc = 0;
+    std::vector<hc> tmp;
+    for (int half = 0; half < 2 && !rc; half++) {
+        s_restrictMask = 1ULL << bit; s_restrictVals = half ? s_restrictMask : 0;
+        std::vector<QOp> queue = ops, merged; std::vector<Pass> passes;
+        plan_passes(queue, true, merged, passes);
+        planned = (int)merged.size();
+        for (const Pass& p : passes) {
+            const bool direct = (p.high == PASS_DIRECT) || (p.high == PASS_PGROUP) || (p.opIdx.size() == 1 && merged[p.opIdx[0]].kind != OP_STAR && merged[p.opIdx[0]].kind != OP_HSTAR);
+            if (direct) {          // the product adds the restriction as a control (run_direct) or as a fixed coset bit (coset kernel)
+                tmp.resize(state.size());
+                for (size_t i = 0; i < state.size(); i++) tmp[i] = tohc(state[i]);
+                for (int idx : p.opIdx) {
+                    QOp o = merged[idx];
+                    if (o.kind == OP_STAR || o.kind == OP_HSTAR) {      // host_apply knows no controlled stars: split the halves by hand
+                        std::vector<hc> full = tmp; host_apply(full, o);
+                        for (size_t i = 0; i < tmp.size(); i++) if ((((unsigned long long)i >> bit) & 1ULL) == (unsigned long long)half) tmp[i] = full[i];
+                    } else { o.ctrlMask |= s_restrictMask; o.ctrlVals |= s_restrictVals; host_apply(tmp, o); }
+                }
+                for (size_t i = 0; i < state.size(); i++) state[i] = mk(tmp[i].real(), tmp[i].imag());
+                continue;
+            }
+            Emitted E;
+            emit_pass(&q, merged, p, E, true);
+            if (E.hdrs[0].numTiles != ((qindex)1 << (n - TILE_BITS - 1))) { rc = -4; break; }       // the other half must be pruned
+            emulate_pass(state, E, 0);
+            tilePasses++;
+        }
+    }
+    s_restrictMask = s_restrictVals = 0;
+    if (rc) return rc;
+    double err = 0, norm = 0;
+    for (size_t i = 0; i < ref.size(); i++) { err = std::max(err, std::abs(ref[i] - tohc(state[i]))); norm = std::max(norm, std::abs(ref[i])); }
+    if (maxErr) *maxErr = norm > 0 ? err / norm : err;
+    if (numTilePasses) *numTilePasses = tilePasses;
+    if (numOpsPlanned) *numOpsPlanned = planned;
     return 0;
 }
 #endif  // QB_SELFTEST

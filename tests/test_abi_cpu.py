@@ -161,3 +161,23 @@ def test_single_precision_reference_pins_to_double_reference():
     outs = H.run_programs("ref32", fx["programs"][:4])
     for got, want in zip(outs, fx["outputs"][:4]):
         H.assert_outputs_match(got, want, tol=2e-5, label="fp32 reference vs fp64 golden")
+
+
+@pytest.mark.parametrize("n,bit", [(13, 12), (13, 6), (14, 7), (16, 15), (17, 9)])
+def test_restricted_flush_on_host(n, bit):
+    """the half-shard flush that the exchange / compute overlap relies on (qb_tile_flush_restricted): gates that never touch
+    index bit `bit`, run first on the half with bit == 0 and then on the half with bit == 1 -- through the planner, emit_pass
+    and the kernel's own round driver on the host -- must equal plain application; the other half's tiles must be pruned,
+    and absorption / star merging must survive the restriction"""
+    lib = capi.selftest_lib()
+    err, passes, planned = C.c_double(), C.c_int(), C.c_int()
+    # bits 0..5 belong to every tile and cannot be restricted by tile pruning: refused (the shim only overlaps on bits >= 10)
+    assert lib.qb_selftest_restricted_flush(n, 10, 1, 3, C.byref(err), C.byref(passes), C.byref(planned)) == -5
+    total_passes = 0
+    for seed in range(5):
+        rc = lib.qb_selftest_restricted_flush(n, 120, 9300 + seed, bit, C.byref(err), C.byref(passes), C.byref(planned))
+        assert rc == 0, f"restricted flush self-test failed structurally (rc={rc})"
+        assert err.value <= 1e-12, f"n={n} bit={bit} seed={seed}: halves differ from plain application by {err.value:.3e}"
+        assert planned.value < 120 + 60          # (QFT-like stages expand to several queued gates; merging must shrink them again)
+        total_passes += passes.value
+    assert total_passes > 0
