@@ -4,6 +4,8 @@
 
 #define PG_K 5                       // independent X/Y masks per pass (2^PG_K amplitudes per thread: 32 = 128 registers)
 #define PG_AMPS (1 << PG_K)
+#define PG_K_GADGET 4                // gadgets per pass chosen by the planner: ncu, 28 qubits: K=4 1.303 ms per pass (6.55 TB/s, 0.326 ms per gadget),
+                                     // K=5 1.895 ms (4.5 TB/s at 192 registers per thread, 0.379 ms per gadget)
 #define PG_K_EXPEC 4                 // expectation terms per pass: measured faster than 5 (32.7 vs 45.0 ms for 200 terms at 28 qubits: occupancy)
 #define PG_MAX_OPS 12                // gadgets per pass: PG_K non-diagonal ones plus diagonal ones riding along
 

@@ -55,7 +55,7 @@
 #define TILE_MAX_CHUNKS (1 << (TILE_BITS - TILE_LOW))
 #define MAX_OPS_PER_PASS 48
 #define QUEUE_MAX 2048                 // deferred gates before a forced flush (cfg 2 issues 680 per step)
-#define PAULI_STREAM_FLUSH 50           // see enqueue(): early flush of pure wide-Pauli streams (a multiple of PG_K)
+#define PAULI_STREAM_FLUSH 48           // see enqueue(): early flush of pure wide-Pauli streams (a multiple of PG_K_GADGET)
 #define FUSE_MIN_LOG_AMPS 13          // smaller states use the direct kernels immediately
 #define STAR_SEGS 6                   // external-control tables: 6 segments x 6 bits of the global index
 
@@ -1169,7 +1169,7 @@ static void plan_passes(std::vector<QOp>& ops, bool reorder, std::vector<QOp>& m
                     const QOp& o = merged[remaining[take]];
                     if (o.ctrlMask || (o.kind != OP_PAULI && o.kind != OP_PARITY)) break;
                     if (o.kind == OP_PAULI) {
-                        if (nm == PG_K) break;
+                        if (nm == PG_K_GADGET) break;
                         masks[nm] = o.maskA;
                         if (pg_rank(masks, nm + 1, nullptr) != nm + 1) break;
                         nm++;
