@@ -49,7 +49,7 @@ kernels: $(LIBDIR)/libquest_b200.so selftest
 # test-only twin of the kernel library: the two translation units that hold host-side self-tests are recompiled with
 # -DQB_SELFTEST (include/quest_b200_selftest.h); the product library above is built WITHOUT them
 selftest: $(LIBDIR)/libquest_b200_selftest.so
-SELFTEST_UNITS := qb_tile qb_runtime
+SELFTEST_UNITS := qb_tile qb_runtime qb_pauli_group
 SELFTEST_OBJS  := $(patsubst %,$(BUILD)/selftest/%.o,$(SELFTEST_UNITS))
 $(BUILD)/selftest/%.o: quest_b200/csrc/%.cu $(CU_HDRS) include/quest_b200_selftest.h
 	@mkdir -p $(dir $@)

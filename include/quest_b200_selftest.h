@@ -14,6 +14,7 @@ int         qb_selftest_bitins(const int* qubits, const int* states, int n, qb_i
 int         qb_selftest_planner(int numQubits, int numOps, unsigned seed, int reorder, double* maxErr, int* numPasses, int* numRounds, int* numOpsPlanned); /* host-only: random gate list applied in program order vs in the tile planner's order (absorbed, merged, re-ordered) on a small host state */
 int         qb_selftest_tile_emulation(int numQubits, int numOps, unsigned seed, int reorder, double* maxErr, int* numTilePasses, int* numDirectOps); /* host-only: planner + emit_pass descriptors + the kernel's own round driver and gate bodies (compiled for the host) vs gate-by-gate application */
 int         qb_selftest_restricted_flush(int numQubits, int numOps, unsigned seed, int bit, double* maxErr, int* numTilePasses, int* numOpsPlanned); /* host-only: the half-shard (restricted) flush behind the exchange/compute overlap == plain application */
+int         qb_selftest_pauli_group(int numQubits, int numOps, unsigned seed, int restrictBit, double* maxErr, int* numPasses); /* host-only: the coset kernel's body + descriptors vs the pair-by-pair definition (restrictBit < 0: whole state) */
 #ifdef __cplusplus
 }
 #endif

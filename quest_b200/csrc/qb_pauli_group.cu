@@ -29,8 +29,19 @@ struct PGDev {
 };
 
 // gadget on register bit T: a_g' = c a_g + f s(idx_g1) a_g1,  a_g1' = c a_g1 + f s(idx_g) a_g   (OpPauliA, qb_gates.cu)
+// one coset: the body of a thread of k_pauli_group, compiled for the host as well (qb_selftest_pauli_group emulates the
+// kernel representative by representative on the CPU)
+#ifdef __CUDA_ARCH__
+#define PG_LD(p) ld_stream(p)
+#define PG_ST(p, v) st_stream(p, v)
+#define PG_POPC(x) __popcll(x)
+#else
+#define PG_LD(p) (*(p))
+#define PG_ST(p, v) (*(p) = (v))
+#define PG_POPC(x) __builtin_popcountll(x)
+#endif
 template <int A, int T>
-__device__ __forceinline__ void pg_pair(cplx (&v)[A], cplx c, cplx f, unsigned par) {
+__host__ __device__ __forceinline__ void pg_pair_hd(cplx (&v)[A], cplx c, cplx f, unsigned par) {
 #pragma unroll
     for (int g = 0; g < A; g++) {
         if (g & (1 << T)) continue;
@@ -43,28 +54,23 @@ __device__ __forceinline__ void pg_pair(cplx (&v)[A], cplx c, cplx f, unsigned p
 }
 
 template <int K>
-__global__ void __launch_bounds__(128) k_pauli_group(cplx* __restrict__ amps, qindex numGroups, const PGDev* __restrict__ gp) {
+__host__ __device__ __forceinline__ void pg_coset(cplx* __restrict__ amps, qindex n, const PGDev& p) {
     constexpr int A = 1 << K;
-    __shared__ PGDev p;
-    for (int i = threadIdx.x; i < (int)(sizeof(PGDev) / 4); i += blockDim.x) ((int*)&p)[i] = ((const int*)gp)[i];
-    __syncthreads();
-    const qindex n = (qindex)blockIdx.x * blockDim.x + threadIdx.x;
-    if (n >= numGroups) return;
     const qindex base = p.ins(n);
     cplx v[A];
 #pragma unroll
-    for (int g = 0; g < A; g++) v[g] = ld_stream(amps + (base ^ p.xr[g]));
+    for (int g = 0; g < A; g++) v[g] = PG_LD(amps + (base ^ p.xr[g]));
     const int numOps = p.numOps;
     for (int o = 0; o < numOps; o++) {
         const PGDevOp op = p.ops[o];
         // parity of (index & yz) per register: that of the representative, flipped where the register's offset says so
-        const unsigned par = ((__popcll((unsigned long long)(base & op.yz)) & 1) ? ~op.sgn : op.sgn);
+        const unsigned par = ((PG_POPC((unsigned long long)(base & op.yz)) & 1) ? ~op.sgn : op.sgn);
         switch (op.slot) {
-        case 0: pg_pair<A, 0>(v, op.c, op.f, par); break;
-        case 1: if (K > 1) pg_pair<A, (K > 1 ? 1 : 0)>(v, op.c, op.f, par); break;
-        case 2: if (K > 2) pg_pair<A, (K > 2 ? 2 : 0)>(v, op.c, op.f, par); break;
-        case 3: if (K > 3) pg_pair<A, (K > 3 ? 3 : 0)>(v, op.c, op.f, par); break;
-        case 4: if (K > 4) pg_pair<A, (K > 4 ? 4 : 0)>(v, op.c, op.f, par); break;
+        case 0: pg_pair_hd<A, 0>(v, op.c, op.f, par); break;
+        case 1: if (K > 1) pg_pair_hd<A, (K > 1 ? 1 : 0)>(v, op.c, op.f, par); break;
+        case 2: if (K > 2) pg_pair_hd<A, (K > 2 ? 2 : 0)>(v, op.c, op.f, par); break;
+        case 3: if (K > 3) pg_pair_hd<A, (K > 3 ? 3 : 0)>(v, op.c, op.f, par); break;
+        case 4: if (K > 4) pg_pair_hd<A, (K > 4 ? 4 : 0)>(v, op.c, op.f, par); break;
         default:                                           // diagonal: v_g *= (parity ? f : c)
 #pragma unroll
             for (int g = 0; g < A; g++) v[g] = cmul(v[g], ((par >> g) & 1u) ? op.f : op.c);
@@ -72,7 +78,17 @@ __global__ void __launch_bounds__(128) k_pauli_group(cplx* __restrict__ amps, qi
         }
     }
 #pragma unroll
-    for (int g = 0; g < A; g++) st_stream(amps + (base ^ p.xr[g]), v[g]);
+    for (int g = 0; g < A; g++) PG_ST(amps + (base ^ p.xr[g]), v[g]);
+}
+
+template <int K>
+__global__ void __launch_bounds__(128) k_pauli_group(cplx* __restrict__ amps, qindex numGroups, const PGDev* __restrict__ gp) {
+    __shared__ PGDev p;
+    for (int i = threadIdx.x; i < (int)(sizeof(PGDev) / 4); i += blockDim.x) ((int*)&p)[i] = ((const int*)gp)[i];
+    __syncthreads();
+    const qindex n = (qindex)blockIdx.x * blockDim.x + threadIdx.x;
+    if (n >= numGroups) return;
+    pg_coset<K>(amps, n, p);
 }
 
 // expectation terms: term t pairs register g with g ^ (1 << t); raw sums as qb_statevec_calcExpecPauliStrBatch_subA defines them
@@ -193,12 +209,13 @@ static unsigned pg_sign_bits(const PGDev& h, unsigned long long yz) {
 
 // applies `numOps` control-free Pauli gadgets / tensors (xy != 0) and parity phase gadgets (xy == 0, yz = target mask) in
 // order, in one pass.  The non-zero xy masks must be linearly independent (at most PG_K of them).
-int qb_pauli_group_apply(const qb_state* q, const PGOp* ops, int numOps, unsigned long long restrictMask, unsigned long long restrictVals) {
+// host: the pass descriptor of a gadget group (pivots, coset offsets, per-op sign bits); returns k through *kOut
+static int pg_describe(const qb_state* q, const PGOp* ops, int numOps, unsigned long long restrictMask, unsigned long long restrictVals, PGDev& h, int* kOut) {
     QB_REQUIRE(numOps >= 1 && numOps <= PG_MAX_OPS, "pauli group: bad op count");
     unsigned long long xy[PG_K]; int k = 0;
     for (int i = 0; i < numOps; i++) if (ops[i].xy) { QB_REQUIRE(k < PG_K, "pauli group: too many X/Y masks"); xy[k++] = ops[i].xy; }
     QB_REQUIRE(k >= 1, "pauli group: needs at least one non-diagonal op");
-    PGDev h; int r = pg_build(q, xy, k, h, restrictMask, restrictVals); if (r) return r;
+    int r = pg_build(q, xy, k, h, restrictMask, restrictVals); if (r) return r;
     h.numOps = numOps;
     int slot = 0;
     for (int i = 0; i < numOps; i++) {
@@ -206,6 +223,13 @@ int qb_pauli_group_apply(const qb_state* q, const PGOp* ops, int numOps, unsigne
         d.slot = ops[i].xy ? slot++ : -1;
         d.yz = (qindex)ops[i].yz; d.sgn = pg_sign_bits(h, ops[i].yz); d.c = ops[i].c; d.f = ops[i].f;
     }
+    *kOut = k;
+    return 0;
+}
+
+int qb_pauli_group_apply(const qb_state* q, const PGOp* ops, int numOps, unsigned long long restrictMask, unsigned long long restrictVals) {
+    PGDev h; int k = 0;
+    int r = pg_describe(q, ops, numOps, restrictMask, restrictVals, h, &k); if (r) return r;
     const PGDev* dev; r = pg_upload(h, &dev); if (r) return r;
     const qindex groups = q->numAmpsPerNode >> (k + __builtin_popcountll(restrictMask));
     const unsigned grid = (unsigned)((groups + 127) / 128);
@@ -244,3 +268,91 @@ int qb_pauli_group_expec(const qb_state* q, const unsigned long long* masks, int
     QB_LAUNCH_CHECK();
     return 0;
 }
+
+#ifdef QB_SELFTEST
+// ------------------------------------------------------------------------------------------
+// host emulation of the coset kernel (no CUDA): random control-free Pauli gadgets and parity gadgets are grouped as the
+// planner groups them (linearly independent X/Y masks, at most PG_K_GADGET per pass), each group's descriptor is built by
+// the product's own pg_describe and run coset by coset through the kernel's own body (pg_coset, compiled for the host), on
+// the whole state or restricted to half of it; the result must equal pair-by-pair application of the definition
+// (cpu_subroutines.cpp:804-905).  tests/test_abi_cpu.py
+// ------------------------------------------------------------------------------------------
+#include <complex>
+#include <random>
+#include <vector>
+#include "../../include/quest_b200_selftest.h"
+extern "C" int qb_selftest_pauli_group(int numQubits, int numOps, unsigned seed, int restrictBit, double* maxErr, int* numPasses) {
+    if (numQubits < 3 || numQubits > 20 || numOps < 1 || restrictBit >= numQubits) return -1;
+    typedef std::complex<double> hc;
+    const int n = numQubits;
+    std::mt19937_64 rng(seed);
+    auto unif = [&]() { return (double)(rng() >> 11) * (1.0 / 9007199254740992.0); };
+    const unsigned long long all = ((1ULL << n) - 1) & ~(restrictBit >= 0 ? (1ULL << restrictBit) : 0ULL);
+    std::vector<PGOp> ops;
+    for (int i = 0; i < numOps; i++) {
+        PGOp o; o.xy = (rng() & rng()) & all; o.yz = (rng() & rng()) & all;          // ~1/4 of the sites each
+        if (rng() % 5 == 0) o.xy = 0;                                                // a diagonal (parity) gadget
+        if (rng() % 7 == 0 && !ops.empty()) o.xy = ops.back().xy;                    // a repeated string: dependent mask
+        o.c = mk(2 * unif() - 1, 2 * unif() - 1); o.f = mk(2 * unif() - 1, 2 * unif() - 1);
+        ops.push_back(o);
+    }
+    std::vector<hc> ref((size_t)1 << n);
+    for (auto& v : ref) v = hc(2 * unif() - 1, 2 * unif() - 1);
+    std::vector<cplx> state(ref.size());
+    for (size_t i = 0; i < ref.size(); i++) state[i] = mk(ref[i].real(), ref[i].imag());
+    auto inHalf = [&](unsigned long long i, int half) { return restrictBit < 0 || (int)((i >> restrictBit) & 1ULL) == half; };
+    // the definition, on the (possibly restricted) index set; both halves in turn when restricted
+    for (const PGOp& o : ops) {
+        const hc c(o.c.x, o.c.y), f(o.f.x, o.f.y);
+        if (!o.xy) { for (size_t i = 0; i < ref.size(); i++) ref[i] *= __builtin_parityll(i & o.yz) ? f : c; continue; }
+        const int h = 63 - __builtin_clzll(o.xy);
+        for (unsigned long long i = 0; i < ref.size(); i++) if (!((i >> h) & 1)) {
+            const unsigned long long w = i ^ o.xy;
+            const double si = __builtin_parityll(i & o.yz) ? -1.0 : 1.0, sw = __builtin_parityll(w & o.yz) ? -1.0 : 1.0;
+            const hc x = ref[i], y = ref[w];
+            ref[i] = c * x + f * sw * y; ref[w] = c * y + f * si * x;
+        }
+    }
+    qb_state q; memset(&q, 0, sizeof q); q.numAmpsPerNode = 1LL << n; q.logNumAmpsPerNode = n; q.numQubits = n;
+    int passes = 0;
+    for (int half = 0; half < (restrictBit >= 0 ? 2 : 1); half++) {
+        size_t i = 0;
+        while (i < ops.size()) {
+            // the planner's grouping rule (qb_tile.cu plan_passes): program order, independent masks, <= PG_K_GADGET strings
+            unsigned long long masks[PG_K]; int nm = 0; size_t take = 0;
+            for (; i + take < ops.size() && take < PG_MAX_OPS; take++) {
+                const PGOp& o = ops[i + take];
+                if (o.xy) {
+                    if (nm == PG_K_GADGET) break;
+                    masks[nm] = o.xy;
+                    if (pg_rank(masks, nm + 1, nullptr) != nm + 1) break;
+                    nm++;
+                }
+            }
+            if (nm == 0) {       // only diagonal gadgets left in this stretch: apply them directly
+                for (size_t j = 0; j < take; j++) for (size_t a = 0; a < state.size(); a++) if (inHalf(a, half)) state[a] = cmul(state[a], __builtin_parityll(a & ops[i + j].yz) ? ops[i + j].f : ops[i + j].c);
+                i += take; continue;
+            }
+            PGDev d; int k = 0;
+            const unsigned long long rm = restrictBit >= 0 ? (1ULL << restrictBit) : 0ULL;
+            int r = pg_describe(&q, &ops[i], (int)take, rm, half ? rm : 0ULL, d, &k); if (r) return -2;
+            const qindex groups = q.numAmpsPerNode >> (k + (restrictBit >= 0 ? 1 : 0));
+            for (qindex g = 0; g < groups; g++) {
+                switch (k) {
+                case 1: pg_coset<1>(state.data(), g, d); break;
+                case 2: pg_coset<2>(state.data(), g, d); break;
+                case 3: pg_coset<3>(state.data(), g, d); break;
+                case 4: pg_coset<4>(state.data(), g, d); break;
+                default: pg_coset<5>(state.data(), g, d); break;
+                }
+            }
+            passes++; i += take;
+        }
+    }
+    double err = 0, norm = 0;
+    for (size_t a = 0; a < ref.size(); a++) { err = std::max(err, std::abs(ref[a] - hc(state[a].x, state[a].y))); norm = std::max(norm, std::abs(ref[a])); }
+    if (maxErr) *maxErr = norm > 0 ? err / norm : err;
+    if (numPasses) *numPasses = passes;
+    return 0;
+}
+#endif

@@ -181,3 +181,18 @@ def test_restricted_flush_on_host(n, bit):
         assert planned.value < 120 + 60          # (QFT-like stages expand to several queued gates; merging must shrink them again)
         total_passes += passes.value
     assert total_passes > 0
+
+
+@pytest.mark.parametrize("n,restrict_bit", [(5, -1), (9, -1), (14, -1), (12, 11), (13, 6), (14, 0)])
+def test_coset_pauli_kernel_on_host(n, restrict_bit):
+    """the coset-blocked Pauli kernel without a GPU (quest_b200/csrc/qb_pauli_group.cu): the planner's grouping rule, the
+    product's own descriptor builder (pivots of the masks' echelon form, coset offsets, sign bits) and the kernel's own
+    per-thread body, compiled for the host, against pair-by-pair application of the definition -- on the whole state and
+    restricted to each half of it (the exchange / compute overlap)"""
+    lib = capi.selftest_lib()
+    err, passes = C.c_double(), C.c_int()
+    for seed in range(6):
+        rc = lib.qb_selftest_pauli_group(n, 60, 9700 + seed, restrict_bit, C.byref(err), C.byref(passes))
+        assert rc == 0, f"coset self-test failed structurally (rc={rc})"
+        assert err.value <= 1e-12, f"n={n} restrict={restrict_bit} seed={seed}: coset passes differ from the definition by {err.value:.3e}"
+        assert 0 < passes.value < 60 * (2 if restrict_bit >= 0 else 1)
