@@ -527,7 +527,8 @@ def run_product(args, rank, world, local_rank):
         sc = P.stats()
         Q.syncQuESTEnv(); d.record(); P.barrier()
         sd = P.stats()
-        sections = {"note": "one extra step with a flush after each section (the timed steps plan the whole step at once)",
+        sections = {"note": "one extra step with a flush after each section (the timed steps plan the whole step at once)"
+                            + ("; with --lookahead the shim replays gate calls late, so the split between sections is not meaningful" if os.environ.get("QUEST_B200_LOOKAHEAD", "0") not in ("", "0") else ""),
                     "qft_ms": P.max_over_ranks(a.elapsed_time(b)), "dense_ms": P.max_over_ranks(b.elapsed_time(c)), "restore_ms": P.max_over_ranks(c.elapsed_time(d)),
                     "qft_launches": sb["launches"] - sa["launches"], "dense_launches": sc["launches"] - sb["launches"], "restore_launches": sd["launches"] - sc["launches"],
                     "dense_tile_passes": sc["passes"] - sb["passes"], "dense_rounds": sc["rounds"] - sb["rounds"], "dense_gates_after_absorption": (sc["tile_ops"] - sb["tile_ops"]) + (sc["direct_ops"] - sb["direct_ops"])}
@@ -625,6 +626,7 @@ def run_product(args, rank, world, local_rank):
         detail = {"total_prob_after_run": total_prob, "circuit_gates_per_s": num_gates / (ms_per_step * 1e-3),
                   "parallelism": f"state sharded over {world} GPUs on the top {logw} qubits" if world > 1 else "single GPU",
                   "p2p_nvlink_kernels": bool(P.lib.qb_p2p_is_available()) if world > 1 else None,
+                  "lookahead_window": int(os.environ.get("QUEST_B200_LOOKAHEAD", "0") or 0),
                   "timed_region": f"{args.steps} x (circuit + queue flush) + syncQuESTEnv (canonical qubit order restored), CUDA events, max over ranks"}
         line = {"metric": METRIC, "value": world * num_gates / (ms_per_step * 1e-3), "unit": "gates/s", "n_gpus": world,
                 "steps": args.steps, "warmup": args.warmup, "ms_per_step": ms_per_step, "higher_is_better": True, "scaling": "weak",
@@ -653,7 +655,11 @@ def main():
     ap.add_argument("--no-e2e", action="store_true")
     ap.add_argument("--no-secondary", action="store_true", help="skip the cfg 3/4/5 records")
     ap.add_argument("--workload", default="cfg2", choices=["cfg2", "cfg3"], help="cfg3: 100 random {H,Rx,CompMatr1,CNOT,CompMatr2} gates on initPlusState")
+    ap.add_argument("--lookahead", type=int, default=None,
+                    help="N>1: QUEST_B200_LOOKAHEAD window of the sharding shim (opt-in look-ahead swap-in victim choice; default: the library's, off)")
     args = ap.parse_args()
+    if args.lookahead is not None:
+        os.environ["QUEST_B200_LOOKAHEAD"] = str(args.lookahead)     # read by libQuEST.so at the first gate
 
     rank = int(os.environ.get("RANK", "0"))
     world = int(os.environ.get("WORLD_SIZE", "1"))

@@ -46,11 +46,13 @@
 
 #include "quest_b200.h"
 #include "qubit_map.hpp"
+#include "lookahead.hpp"
 
 #include <algorithm>
 #include <array>
 #include <complex>
 #include <cstdlib>
+#include <functional>
 #include <map>
 #include <unordered_map>
 #include <tuple>
@@ -244,6 +246,35 @@ static bool mapEligible(Qureg q) {
     return relabelEnabled() && q.isGpuAccelerated && !q.isDensityMatrix && q.gpuAmps != nullptr && q.numQubits <= 62;
 }
 
+
+/*
+ * LOOK-AHEAD VICTIM CHOICE (opt-in: QUEST_B200_LOOKAHEAD=<window>; 0 = off = default) -- see lookahead.hpp
+ */
+
+static int lookaheadWindow() {
+    static int w = -1;
+    if (w < 0) { const char* e = std::getenv("QUEST_B200_LOOKAHEAD"); w = e ? std::atoi(e) : 0; if (w < 0) w = 0; if (w > 4096) w = 4096; }
+    return w;
+}
+
+static qb_lookahead::GateLog& gateLog() {
+    static qb_lookahead::GateLog log(lookaheadWindow());
+    return log;
+}
+
+static bool deferEligible(Qureg q) {
+    return lookaheadWindow() > 0 && !gateLog().replaying() && !g_inCanonicalise && q.isDistributed && mapEligible(q);
+}
+
+// every path that looks at or changes amplitudes other than through a logged gate comes through here first
+static void drainDeferred() {
+    if (lookaheadWindow() > 0) gateLog().drain();
+}
+
+static void deferGate(Qureg q, std::vector<int> shardTargs, std::function<void()> run, int swapA = -1, int swapB = -1) {
+    gateLog().push(q.gpuAmps, std::move(shardTargs), std::move(run), swapA, swapB);
+}
+
 static QubitMap* findMap(Qureg q) {
     if (g_qubitMaps.empty() || !mapEligible(q)) return nullptr;
     auto it = g_qubitMaps.find(q.gpuAmps);
@@ -301,6 +332,7 @@ static void canonicalise(QubitMap& m) {
 }
 
 static void qbmap_canon(Qureg q) {
+    drainDeferred();
     if (QubitMap* m = findMap(q)) {
         canonicalise(*m);
         g_qubitMaps.erase(q.gpuAmps);
@@ -311,11 +343,13 @@ static void qbmap_canon(Qureg q) {
 }
 
 static void qbmap_reset(Qureg q) {
+    drainDeferred();                    // logged gates act on the state that is about to be overwritten: run them first
     if (!g_qubitMaps.empty() && q.gpuAmps != nullptr) g_qubitMaps.erase(q.gpuAmps);
 }
 
 
 void qbmap_forget(const void* gpuAmps) {
+    drainDeferred();
     if (!g_qubitMaps.empty()) g_qubitMaps.erase(gpuAmps);
     g_rankBitsPinned.erase(gpuAmps);
     g_queuedBits.erase(gpuAmps);
@@ -323,6 +357,7 @@ void qbmap_forget(const void* gpuAmps) {
 }
 
 void qbmap_canonicaliseHolding(const void* gpuPtr) {
+    drainDeferred();
     for (auto it = g_qubitMaps.begin(); it != g_qubitMaps.end(); ++it) {
         const char* lo = reinterpret_cast<const char*>(it->second.qureg.gpuAmps);
         const char* hi = lo + it->second.qureg.numAmpsPerNode * sizeof(qcomp);
@@ -336,6 +371,7 @@ void qbmap_canonicaliseHolding(const void* gpuPtr) {
 // the (process-specific) device pointers that key the table.
 void qbmap_canonicaliseAll() {
     if (g_inCanonicalise) return;
+    drainDeferred();
     std::vector<QubitMap*> order;
     for (auto& kv : g_qubitMaps) order.push_back(&kv.second);
     std::sort(order.begin(), order.end(), [](const QubitMap* a, const QubitMap* b) { return a->seq < b->seq; });
@@ -371,6 +407,12 @@ static bool pullTargetsIntoShard(Qureg qureg, QubitMap& m, vector<int>& targs, c
         int queued = touched != 0;
 
         int victim = -1;
+
+        // replaying a logged window: evict the qubit whose next use inside the shard lies farthest ahead (lookahead.hpp)
+        std::vector<size_t> next;
+        if (lookaheadWindow() > 0 && gateLog().nextShardUses(qureg.gpuAmps, qureg.numQubits, next))
+            victim = qb_lookahead::chooseVictim(next, m.logi, m.lastUse, (unsigned long long) used, touched, nl);
+
         for (int pass = 0; pass < 4 && victim < 0; pass++) {
             bool wantUntouched = (pass < 2) && mayOvertake && queued > 0;
             if (pass < 2 && !wantUntouched) continue;
@@ -951,6 +993,13 @@ void localiser_densmatr_allTargDiagMatr(Qureg qureg, FullStateDiagMatr matr, qco
 
 template <class T>
 void localiser_statevec_anyCtrlAnyTargAnyMatr(Qureg qureg, vector<int> ctrls, vector<int> ctrlStates, vector<int> targs, T matr, bool conj) {
+    if constexpr (!util_isCompMatr<T>() && !util_isDiagMatr<T>())                 // fixed-size matrices are passed by value
+        if (deferEligible(qureg)) {
+            constexpr bool dense = util_isCompMatr1<T>() || util_isCompMatr2<T>();
+            deferGate(qureg, dense ? targs : vector<int>{}, [=]() { localiser_statevec_anyCtrlAnyTargAnyMatr(qureg, ctrls, ctrlStates, targs, matr, conj); });
+            return;
+        }
+    drainDeferred();
     if constexpr (util_isCompMatr<T>() || util_isCompMatr1<T>() || util_isCompMatr2<T>())
         relabelForDenseGate(qureg, ctrls, targs);
     else { QubitMap* m = findMap(qureg); mapQubits(m, ctrls); mapQubits(m, targs); noteGateQubits(qureg, ctrls); noteGateQubits(qureg, targs); }
@@ -1288,6 +1337,7 @@ void localiser_densmatr_partialTrace(Qureg inQureg, Qureg outQureg, vector<int> 
  */
 
 qreal localiser_statevec_calcTotalProb(Qureg qureg) {
+    drainDeferred();
     qreal prob = accel_statevec_calcTotalProb_sub(qureg);
     if (qureg.isDistributed)
         comm_reduceReal(&prob);
@@ -1575,7 +1625,18 @@ void localiser_densmatr_multiQubitProjector(Qureg qureg, vector<int> qubits, vec
  * then run the physical implementation above
  */
 
+static vector<int> pauliShardTargs(PauliStr str, Qureg qureg) {        // X and Y sites: the non-diagonal targets
+    auto [x, y, z] = paulis_getSeparateInds(str, qureg);
+    return util_getConcatenated(x, y);
+}
+
 void localiser_statevec_anyCtrlSwap(Qureg qureg, vector<int> ctrls, vector<int> ctrlStates, int targ1, int targ2) {
+    if (deferEligible(qureg)) {
+        bool relabelOnly = ctrls.empty();
+        deferGate(qureg, {}, [=]() { localiser_statevec_anyCtrlSwap(qureg, ctrls, ctrlStates, targ1, targ2); }, relabelOnly ? targ1 : -1, relabelOnly ? targ2 : -1);
+        return;
+    }
+    drainDeferred();
     if (ctrls.empty() && mapEligible(qureg)) {              // pure relabelling: no amplitude moves
         QubitMap& m = getMap(qureg);
         relabelSwap(m, targ1, targ2);
@@ -1589,23 +1650,30 @@ void localiser_statevec_anyCtrlSwap(Qureg qureg, vector<int> ctrls, vector<int> 
 }
 
 void localiser_statevec_anyCtrlOneTargDenseMatr(Qureg qureg, vector<int> ctrls, vector<int> ctrlStates, int targ, CompMatr1 matr, bool conj) {
+    if (deferEligible(qureg)) { deferGate(qureg, {targ}, [=]() { localiser_statevec_anyCtrlOneTargDenseMatr(qureg, ctrls, ctrlStates, targ, matr, conj); }); return; }
+    drainDeferred();
     vector<int> targs = {targ};
     relabelForDenseGate(qureg, ctrls, targs);
     phys_statevec_anyCtrlOneTargDenseMatr(qureg, ctrls, ctrlStates, targs[0], matr, conj);
 }
 
 void localiser_statevec_anyCtrlTwoTargDenseMatr(Qureg qureg, vector<int> ctrls, vector<int> ctrlStates, int targ1, int targ2, CompMatr2 matr, bool conj) {
+    if (deferEligible(qureg)) { deferGate(qureg, {targ1, targ2}, [=]() { localiser_statevec_anyCtrlTwoTargDenseMatr(qureg, ctrls, ctrlStates, targ1, targ2, matr, conj); }); return; }
+    drainDeferred();
     vector<int> targs = {targ1, targ2};
     relabelForDenseGate(qureg, ctrls, targs);
     phys_statevec_anyCtrlTwoTargDenseMatr(qureg, ctrls, ctrlStates, targs[0], targs[1], matr, conj);
 }
 
 void localiser_statevec_anyCtrlAnyTargDenseMatr(Qureg qureg, vector<int> ctrls, vector<int> ctrlStates, vector<int> targs, CompMatr matr, bool conj) {
+    drainDeferred();                    // (heap matrix: never logged)
     relabelForDenseGate(qureg, ctrls, targs);
     phys_statevec_anyCtrlAnyTargDenseMatr(qureg, ctrls, ctrlStates, targs, matr, conj);
 }
 
 void localiser_statevec_anyCtrlOneTargDiagMatr(Qureg qureg, vector<int> ctrls, vector<int> ctrlStates, int targ, DiagMatr1 matr, bool conj) {
+    if (deferEligible(qureg)) { deferGate(qureg, {}, [=]() { localiser_statevec_anyCtrlOneTargDiagMatr(qureg, ctrls, ctrlStates, targ, matr, conj); }); return; }
+    drainDeferred();
     QubitMap* m = findMap(qureg);
     mapQubits(m, ctrls);
     int t = mapQubit(m, targ);
@@ -1614,6 +1682,8 @@ void localiser_statevec_anyCtrlOneTargDiagMatr(Qureg qureg, vector<int> ctrls, v
 }
 
 void localiser_statevec_anyCtrlTwoTargDiagMatr(Qureg qureg, vector<int> ctrls, vector<int> ctrlStates, int targ1, int targ2, DiagMatr2 matr, bool conj) {
+    if (deferEligible(qureg)) { deferGate(qureg, {}, [=]() { localiser_statevec_anyCtrlTwoTargDiagMatr(qureg, ctrls, ctrlStates, targ1, targ2, matr, conj); }); return; }
+    drainDeferred();
     QubitMap* m = findMap(qureg);
     mapQubits(m, ctrls);
     int t1 = mapQubit(m, targ1), t2 = mapQubit(m, targ2);
@@ -1622,6 +1692,7 @@ void localiser_statevec_anyCtrlTwoTargDiagMatr(Qureg qureg, vector<int> ctrls, v
 }
 
 void localiser_statevec_anyCtrlAnyTargDiagMatr(Qureg qureg, vector<int> ctrls, vector<int> ctrlStates, vector<int> targs, DiagMatr matr, qcomp exponent, bool conj) {
+    drainDeferred();                    // (heap matrix: never logged)
     QubitMap* m = findMap(qureg);
     mapQubits(m, ctrls);
     mapQubits(m, targs);
@@ -1630,11 +1701,15 @@ void localiser_statevec_anyCtrlAnyTargDiagMatr(Qureg qureg, vector<int> ctrls, v
 }
 
 void localiser_statevec_anyCtrlPauliTensor(Qureg qureg, vector<int> ctrls, vector<int> ctrlStates, PauliStr str, qcomp factor) {
+    if (deferEligible(qureg)) { deferGate(qureg, pauliShardTargs(str, qureg), [=]() { localiser_statevec_anyCtrlPauliTensor(qureg, ctrls, ctrlStates, str, factor); }); return; }
+    drainDeferred();
     relabelForPauli(qureg, ctrls, str);
     phys_statevec_anyCtrlPauliTensor(qureg, ctrls, ctrlStates, str, factor);
 }
 
 void localiser_statevec_anyCtrlPhaseGadget(Qureg qureg, vector<int> ctrls, vector<int> ctrlStates, vector<int> targs, qreal phase) {
+    if (deferEligible(qureg)) { deferGate(qureg, {}, [=]() { localiser_statevec_anyCtrlPhaseGadget(qureg, ctrls, ctrlStates, targs, phase); }); return; }
+    drainDeferred();
     QubitMap* m = findMap(qureg);
     mapQubits(m, ctrls);
     mapQubits(m, targs);
@@ -1643,16 +1718,20 @@ void localiser_statevec_anyCtrlPhaseGadget(Qureg qureg, vector<int> ctrls, vecto
 }
 
 void localiser_statevec_anyCtrlPauliGadget(Qureg qureg, vector<int> ctrls, vector<int> ctrlStates, PauliStr str, qreal phase) {
+    if (deferEligible(qureg)) { deferGate(qureg, pauliShardTargs(str, qureg), [=]() { localiser_statevec_anyCtrlPauliGadget(qureg, ctrls, ctrlStates, str, phase); }); return; }
+    drainDeferred();
     relabelForPauli(qureg, ctrls, str);
     phys_statevec_anyCtrlPauliGadget(qureg, ctrls, ctrlStates, str, phase);
 }
 
 qreal localiser_statevec_calcProbOfMultiQubitOutcome(Qureg qureg, vector<int> qubits, vector<int> outcomes) {
+    drainDeferred();
     mapQubits(findMap(qureg), qubits);
     return phys_statevec_calcProbOfMultiQubitOutcome(qureg, qubits, outcomes);
 }
 
 void localiser_statevec_multiQubitProjector(Qureg qureg, vector<int> qubits, vector<int> outcomes, qreal prob) {
+    drainDeferred();
     mapQubits(findMap(qureg), qubits);
     phys_statevec_multiQubitProjector(qureg, qubits, outcomes, prob);
 }

@@ -60,6 +60,9 @@ def main():
             out["transport"] = int(core.qb_comm_transport())
             core.qb_p2p_overlapped_count.restype = ctypes.c_ulonglong
             out["overlapped_swaps"] = int(core.qb_p2p_overlapped_count(1))
+            nex = ctypes.c_ulonglong(0)
+            core.qb_p2p_stats(ctypes.byref(nex), None)
+            out["p2p_exchanges"] = int(nex.value)          # cumulative over the programs this worker has run
         outs.append(out)
     Q.finalizeQuESTEnv()
     pickle.dump(outs, open(dst, "wb"))

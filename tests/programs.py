@@ -419,3 +419,26 @@ def coevolution_program(n, seed, num_ops=60):
     ops.append(["calcTotalProb", "phi"])
     return {"quregs": {"psi": {"n": n, "init": "zero"}, "rho": {"n": n, "dm": 1, "init": "zero"}, "phi": {"n": n, "init": "plus"}},
             "ops": ops, "dump": ["psi", "rho", "phi"]}
+
+
+def two_quregs_program(n, seed_a, seed_b, num_ops=40):
+    """two statevectors evolved in lock-step with a syncQuESTEnv() in the middle and at the end (with several GPUs: two live
+    qubit maps, restored in creation order on every rank)"""
+    a, b = relabel_program(n, seed_a, num_ops=num_ops, reads=False), relabel_program(n, seed_b, num_ops=num_ops, reads=False)
+    ops = []
+    for x, y in zip(a["ops"], b["ops"]):
+        ops.append(x)
+        ops.append([y[0], "chi"] + list(y[2:]))
+    ops.insert(len(ops) // 2, ["syncQuESTEnv"])
+    ops.append(["syncQuESTEnv"])
+    return {"quregs": {"psi": a["quregs"]["psi"], "chi": b["quregs"]["psi"]}, "ops": ops, "dump": ["psi", "chi"]}
+
+
+def lookahead_programs(logp):
+    """what the look-ahead gate log (quest_b200/shim/lookahead.hpp) has to survive: reads and canonical-order restores in
+    the middle of a logged window, heap matrices (never logged), measurements, Pauli gadgets, a gate-only stretch several
+    windows long, two Quregs sharing the one log"""
+    return [relabel_program(logp + 7, 6302), relabel_program(logp + 13, 6303, num_ops=120),
+            relabel_program(logp + 13, 6304, num_ops=600, reads=False), cfg2_program(logp + 13, 6403, 40),
+            measurement_program(logp + 5, 6102), cfg5_program(logp + 6, 6103, num_terms=30),
+            two_quregs_program(logp + 13, 6601, 6602)]

@@ -115,13 +115,23 @@ def test_two_relabelled_quregs_and_sync(world):
     """two distributed statevectors with live qubit maps, restored by syncQuESTEnv() in creation order on every rank
     (ADVICE r1, medium), and interleaved gates on several Quregs"""
     logp = world.bit_length() - 1
-    n = logp + 13
-    a, b = P.relabel_program(n, 6601, num_ops=40, reads=False), P.relabel_program(n, 6602, num_ops=40, reads=False)
-    ops = []
-    for x, y in zip(a["ops"], b["ops"]):
-        ops.append(x)
-        ops.append([y[0], "chi"] + list(y[2:]))
-    ops.insert(len(ops) // 2, ["syncQuESTEnv"])
-    ops.append(["syncQuESTEnv"])
-    prog = {"quregs": {"psi": a["quregs"]["psi"], "chi": b["quregs"]["psi"]}, "ops": ops, "dump": ["psi", "chi"]}
-    _check([prog], world)
+    _check([P.two_quregs_program(logp + 13, 6601, 6602)], world)
+
+
+def _exchanges_of(outs, k):
+    """exchanges program k issued (the workers report a cumulative counter)"""
+    return outs[k]["p2p_exchanges"] - (outs[k - 1]["p2p_exchanges"] if k else 0)
+
+
+@pytest.mark.skipif(not WORLDS, reason="needs a GPU")
+@pytest.mark.parametrize("world", WORLDS[1:2])
+def test_look_ahead_victim_choice_sharded(world):
+    """QUEST_B200_LOOKAHEAD=W (opt-in): gate calls are logged and replayed W gates late so that a swap-in can evict the
+    qubit needed farthest in the future (quest_b200/shim/lookahead.hpp).  Same results as the reference through reads,
+    restores, heap matrices, measurements and two Quregs sharing the log -- and no more exchanges than the default rule
+    on the gate-only stretch (4 ranks, window 8: 86 against 107, profiles/r2_lookahead_gpu_check.txt)"""
+    logp = world.bit_length() - 1
+    progs = P.lookahead_programs(logp)
+    got = _check(progs, world, env={"QUEST_B200_LOOKAHEAD": "8"})
+    base = H.run_programs_distributed(progs, world)
+    assert _exchanges_of(got, 2) <= _exchanges_of(base, 2), "look-ahead cost exchanges on a gate-only program"
